@@ -1,0 +1,149 @@
+/*
+ * mjrl_b200 -- C ABI of the B200-native NPG/TRPO/DAPG post-rollout update engine.
+ *
+ * The reference (aravindr93/mjrl) is pure Python and has no FFI of its own; the boundary it exposes
+ * is Python duck-typing.  This header is the C ABI that sits *underneath*
+ * the Python classes in mjrl_b200/ (which keep the reference signatures).  Every entry point below
+ * cites the reference function(s) it replaces, relative to /root/reference/mjrl/.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types;
+ *   - every call returns 0 on success, <0 on error (mjb_last_error() gives the text);
+ *   - "host-or-device" float vectors go through cudaMemcpyDefault (UVA), either kind is accepted;
+ *   - one engine per device; calls on one engine must not be concurrent (mjrl is single-threaded);
+ *   - calls are asynchronous on the engine's stream unless they return host scalars/arrays
+ *     (those synchronise the stream before returning);
+ *   - no CPU fallback anywhere: a missing GPU / failed launch is an error code.
+ */
+#ifndef MJRL_B200_H
+#define MJRL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MJB_VERSION 1
+
+typedef struct mjb_engine mjb_engine;
+
+typedef struct mjb_config {
+    int32_t device;          /* CUDA ordinal */
+    int32_t obs_dim;         /* env_spec.observation_dim            (utils/gym_env.py:9-13)            */
+    int32_t act_dim;         /* env_spec.action_dim  (<= 32)                                            */
+    int32_t n_hidden;        /* 0 = LinearPolicy (policies/gaussian_linear.py:32), 2 = MLP              */
+    int32_t hidden[2];       /* MLP hidden sizes (policies/gaussian_mlp.py:9), each <= 256              */
+    int32_t vf_hidden[2];    /* MLPBaseline hidden sizes (baselines/mlp_baseline.py:12), each <= 256    */
+    float   min_log_std;     /* policies/gaussian_mlp.py:10                                             */
+    int64_t max_samples;     /* capacity: rollout + demo timesteps held by this rank                    */
+    int32_t max_paths;       /* capacity: trajectories held by this rank                                */
+    int32_t world_size;      /* data-parallel ranks (1 = single GPU)                                    */
+    int32_t rank;
+} mjb_config;
+
+/* Scalars the reference logs after train_from_paths (algos/npg_cg.py:145-151, trpo.py:129-135). */
+typedef struct mjb_step_stats {
+    double alpha, delta, kl_dist, surr_before, surr_after;
+    double vpg_dot_npg;      /* g . x                                                                   */
+    int32_t backtracks;      /* TRPO line-search shrinks (trpo.py:108-120)                              */
+    int32_t cg_iters_run;    /* FVPs actually evaluated (early exit of utils/cg_solve.py:19-20)         */
+    float time_vpg_ms, time_npg_ms, time_eval_ms;   /* CUDA-event timings of the phases                */
+} mjb_step_stats;
+
+/* Return statistics of the rollout batch (algos/batch_reinforce.py:188-195). */
+typedef struct mjb_batch_stats {
+    double mean_return, std_return, min_return, max_return;
+    double adv_mean, adv_std;   /* pre-whitening advantage moments (population std)                     */
+    int64_t n_samples_global;
+} mjb_batch_stats;
+
+enum { MJB_ALGO_NPG = 0, MJB_ALGO_TRPO = 1, MJB_ALGO_DAPG = 2 };
+enum { MJB_BATCH_ROLLOUT = 0, MJB_BATCH_DEMO = 1 };
+
+int  mjb_version(void);
+const char* mjb_last_error(const mjb_engine* e);   /* e may be NULL: error of the last failed create  */
+
+int  mjb_create(const mjb_config* cfg, mjb_engine** out);
+void mjb_destroy(mjb_engine* e);
+int  mjb_synchronize(mjb_engine* e);
+
+/* ---- multi-GPU: one process per GPU; NCCL communicator owned by the engine -------------------- */
+/* rank 0 obtains a 128-byte NCCL unique id, the host side broadcasts it (torch.distributed), every
+ * rank calls mjb_comm_init.  All reductions below then all-reduce across ranks.         */
+int  mjb_comm_unique_id(void* id128);
+int  mjb_comm_init(mjb_engine* e, const void* id128);
+
+/* ---- trajectories in (samplers/core.py:85-92 path dicts; algos/batch_reinforce.py:180-182 concat) */
+/* Per-path HOST pointers to float64 arrays exactly as the sampler delivers them: obs[i] -> (len[i],
+ * obs_dim), act[i] -> (len[i], act_dim), rew[i] -> (len[i]).  rew may be NULL (demo paths).  Packs
+ * path-order/time-order into device fp32 [N,obs]/[N,act] + fp64 rew through pinned staging.          */
+int  mjb_batch_upload(mjb_engine* e, int which, int32_t n_paths, const double* const* obs,
+                      const double* const* act, const double* const* rew, const int32_t* len,
+                      const uint8_t* terminated);
+/* Same, from already-concatenated host-or-device arrays (fp64 host layout of np.concatenate). */
+int  mjb_batch_upload_flat(mjb_engine* e, int which, int32_t n_paths, const double* obs, const double* act,
+                           const double* rew, const int32_t* len, const uint8_t* terminated);
+/* Advantages computed elsewhere (callers of train_from_paths that bring path["advantages"]). */
+int  mjb_batch_set_advantages(mjb_engine* e, const double* adv_concat);
+int64_t mjb_batch_size(const mjb_engine* e, int which);
+
+/* ---- returns / advantages (utils/process_samples.py:3-35) ----------------------------------- */
+int  mjb_compute_returns(mjb_engine* e, double gamma);                 /* compute_returns :3-5        */
+int  mjb_vf_predict(mjb_engine* e);                                    /* MLPBaseline.predict, all paths (baselines/mlp_baseline.py:97-105) */
+int  mjb_compute_advantages(mjb_engine* e, double gamma, double gae_lambda, int use_gae); /* :7-35    */
+int  mjb_get_returns(mjb_engine* e, double* out);                      /* host-or-device, N doubles   */
+int  mjb_get_baseline(mjb_engine* e, float* out);                      /* N floats                    */
+int  mjb_get_advantages(mjb_engine* e, double* out);                   /* un-whitened, N doubles      */
+int  mjb_get_adv_white(mjb_engine* e, float* out);                     /* after mjb_process_paths     */
+/* concat + whitening + return statistics (algos/batch_reinforce.py:178-197) */
+int  mjb_process_paths(mjb_engine* e, mjb_batch_stats* out);
+
+/* ---- policy parameters (policies/gaussian_mlp.py:60-87; utils/fc_network.py:27-37) ---------- */
+int  mjb_policy_dim(const mjb_engine* e);
+int  mjb_policy_set_params(mjb_engine* e, const float* theta, int set_new, int set_old);   /* clamps log_std */
+int  mjb_policy_get_params(mjb_engine* e, float* theta_out, int which_old);
+int  mjb_policy_set_transforms(mjb_engine* e, const float* in_shift, const float* in_scale,
+                               const float* out_shift, const float* out_scale, int which_old);
+
+/* ---- the differentiable pieces -------------------------------------------------------------- */
+/* CPI_surrogate + kl_old_new fused (algos/batch_reinforce.py:40-52, policies/gaussian_mlp.py:99-145);
+ * out[0] = surrogate, out[1] = mean KL(old||new as the reference defines it). */
+int  mjb_policy_eval(mjb_engine* e, double out[2]);
+/* flat_vpg (algos/batch_reinforce.py:54-58); include_demo: DAPG gradient over rollout+demo with the
+ * weights of algos/dapg.py:62-74 (lam = lam_0*lam_1^iter), already multiplied by sample_coef (:97-98). */
+int  mjb_policy_vpg(mjb_engine* e, int include_demo, double demo_lam, float* g_out);
+/* NPG.HVP (algos/npg_cg.py:62-81): F v + damping v.  idx (device-or-host int32, n_idx entries, global
+ * sample indices) reproduces hvp_sample_frac<0.99 (:65-69); NULL = all samples. */
+int  mjb_policy_fvp(mjb_engine* e, const float* v, float damping, const int32_t* idx, int64_t n_idx,
+                    float* out);
+/* cg_solve (utils/cg_solve.py:3-22) with the FVP above, entirely on device; b = last mjb_policy_vpg
+ * result if b == NULL.  idx: optional [iters][n_idx] subsample indices. */
+int  mjb_policy_cg(mjb_engine* e, const float* b, int iters, float damping, float residual_tol,
+                   const int32_t* idx, int64_t n_idx, float* x_out);
+/* One whole train_from_paths after process_paths: surrogate, VPG, CG, step size, update (+TRPO line
+ * search), re-evaluation, old <- new (algos/npg_cg.py:109-142, trpo.py:83-126, dapg.py:92-121). */
+int  mjb_policy_step(mjb_engine* e, int algo, double step_size_or_kl, double const_learn_rate,
+                     int cg_iters, float damping, double demo_lam, const int32_t* hvp_idx, int64_t n_idx,
+                     mjb_step_stats* out);
+int  mjb_policy_last_vectors(mjb_engine* e, float* vpg_out, float* npg_out);   /* g and x of the last step */
+
+/* ---- MLP baseline (baselines/mlp_baseline.py, utils/optimize_model.py) ---------------------- */
+int  mjb_vf_dim(const mjb_engine* e);
+/* weights / Adam moments in nn.Sequential.parameters() order; step = optimizer step count. */
+int  mjb_vf_set_state(mjb_engine* e, const float* w, const float* m, const float* v, int64_t step);
+int  mjb_vf_get_state(mjb_engine* e, float* w, float* m, float* v, int64_t* step);
+/* MLPBaseline.fit (mlp_baseline.py:61-95): epochs x (int(N/bs)-1) sequential Adam steps on MSE with
+ * L2-in-gradient weight decay; perms = [epochs][N] host int32 permutations (np.random.permutation).
+ * err_out (nullable) = {error_before, error_after} of return_errors=True (:74-83,:87-94). */
+int  mjb_vf_fit(mjb_engine* e, const int32_t* perms, int epochs, int batch_size, float lr, float reg_coef,
+                double err_out[2]);
+
+/* ---- introspection for benchmarks ------------------------------------------------------------ */
+int64_t mjb_kernel_launches(const mjb_engine* e);        /* kernels launched by this engine so far    */
+int  mjb_fvp_timing(mjb_engine* e, float* last_ms);       /* CUDA-event time of the last FVP kernel    */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MJRL_B200_H */

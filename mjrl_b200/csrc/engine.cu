@@ -1,0 +1,919 @@
+// C-ABI implementation (include/mjrl_b200.h): device state, packing, orchestration of the tile kernels,
+// device-resident CG, NPG/TRPO/DAPG step, baseline predict/fit, NCCL data parallelism.
+// No CPU fallback: every entry point needs a CUDA device and returns <0 on failure.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mjrl_b200.h"
+#include "kernels.h"
+
+using namespace mjb;
+
+namespace {
+
+std::string g_create_error;
+
+// ---- NCCL resolved at run time from the library torch already loaded (no link-time dependency) ----
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string& err) {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            lib = dlopen(n, RTLD_NOW | RTLD_NOLOAD);
+            if (!lib) lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) { err = "cannot dlopen libnccl.so.2"; return false; }
+#define MJB_SYM(field, name) \
+    field = reinterpret_cast<decltype(field)>(dlsym(lib, name)); \
+    if (!field) { err = std::string("missing NCCL symbol ") + name; return false; }
+        MJB_SYM(GetUniqueId, "ncclGetUniqueId") MJB_SYM(CommInitRank, "ncclCommInitRank")
+        MJB_SYM(CommDestroy, "ncclCommDestroy") MJB_SYM(AllReduce, "ncclAllReduce")
+        MJB_SYM(Broadcast, "ncclBroadcast") MJB_SYM(GroupStart, "ncclGroupStart")
+        MJB_SYM(GroupEnd, "ncclGroupEnd") MJB_SYM(GetErrorString, "ncclGetErrorString")
+#undef MJB_SYM
+        return true;
+    }
+};
+NcclApi g_nccl;
+
+struct ParamSet {           // one policy parameter set on device
+    float* theta = nullptr;       // flat, reference layout
+    float* prep = nullptr;        // kernel layout
+    float* in_shift = nullptr; float* in_scale = nullptr; float* out_shift = nullptr; float* out_scale = nullptr;
+};
+
+}  // namespace
+
+struct mjb_engine {
+    mjb_config cfg;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    long long launches = 0;
+    // ---- policy
+    bool linear = false;
+    int H = 0;
+    PrepLayout PL;
+    LinLayout LL;
+    int d = 0, prep_total = 0, A = 0, tLS = 0;
+    ParamSet pnew, pold;
+    float* prep_tan = nullptr;
+    bool old_equals_new = true, old_cache_valid = false, transforms_equal = true;
+    long long cache_rows = 0;
+    // ---- batch
+    long long cap = 0;
+    float* obs = nullptr; float* act = nullptr; double* rew = nullptr;
+    int* path_off = nullptr; unsigned char* term = nullptr; int* tstep = nullptr;
+    long long n_roll = 0, n_demo = 0, n_glob_roll = 0;
+    int n_paths = 0, n_glob_paths = 0;
+    std::vector<int> h_path_off;
+    double* ret = nullptr; double* adv = nullptr; float* base = nullptr; float* adv_white = nullptr;
+    float* weights = nullptr; double* path_ret = nullptr;
+    float* ll_old = nullptr; float* mu_old = nullptr;
+    bool have_adv = false, have_white = false;
+    // ---- scratch
+    float* gpartial = nullptr; long long gstride = 0; int max_grid = 0;
+    double* eval_partial = nullptr; double* mom_scratch = nullptr;
+    double* dsc = nullptr;        // small device doubles, see enum below
+    double* h_dsc = nullptr;      // pinned mirror
+    float *g = nullptr, *x = nullptr, *r = nullptr, *p = nullptr, *Fp = nullptr, *tmpv = nullptr;
+    int* idx_dev = nullptr; long long idx_cap = 0;
+    void* pinned = nullptr; size_t pinned_bytes = 0;
+    double* stage64 = nullptr; size_t stage64_elems = 0;
+    int occ[4] = {0, 0, 0, 0};
+    // ---- value net
+    int vfH = 0; PrepLayout VPL; int vf_d = 0;
+    float *vf_w = nullptr, *vf_m = nullptr, *vf_v = nullptr, *vf_wT = nullptr, *vf_prep = nullptr;
+    long long vf_step = 0;
+    int* perm_dev = nullptr; long long perm_cap = 0;
+    // global (all-rank) copies used by the replicated fit when world_size > 1
+    float* fit_obs = nullptr; int* fit_tstep = nullptr; double* fit_ret = nullptr; long long fit_cap = 0;
+    // ---- comm
+    ncclComm_t comm = nullptr;
+    // ---- timing
+    cudaEvent_t ev[6];
+    float last_fvp_ms = 0.f;
+};
+
+enum {  // slots in dsc
+    DS_STATS = 0,      // adv mean, adv std
+    DS_MOM = 2,        // moments scratch out (2)
+    DS_SCALE = 4,      // 1/N_global_rollout, 1/world
+    DS_SCALE_SUB = 6,  // 1/n_idx_global, 1/world
+    DS_CG = 8,         // rdotr, done, iters, -
+    DS_EVAL = 12,      // surr sum, kl sum
+    DS_DOT = 14,       // g.x
+    DS_ALPHA = 15,
+    DS_CNT = 16,       // counts for all-reduce (4)
+    DS_RET = 20,       // path-return stats: sum, sumsq, min, max, n
+    DS_VF = 26,        // vf error sums (2)
+    DS_TOTAL = 32
+};
+
+#define FAIL(e, msg) do { (e)->err = (msg); return -1; } while (0)
+#define CK(e, call) do { cudaError_t _c = (call); if (_c != cudaSuccess) { \
+    (e)->err = std::string(#call) + ": " + cudaGetErrorString(_c); return -1; } } while (0)
+#define NK(e, call) do { ncclResult_t _c = (call); if (_c != ncclSuccess) { \
+    (e)->err = std::string(#call) + ": " + g_nccl.GetErrorString(_c); return -1; } } while (0)
+
+namespace {
+
+int pad_hidden(int h) { return h <= 32 ? 32 : h <= 64 ? 64 : h <= 128 ? 128 : 256; }
+
+cudaError_t launch_mlp_any(int H, int mode, const MlpArgs& a, int grid, cudaStream_t s) {
+    switch (H) {
+        case 32: return launch_mlp_h32(mode, a, grid, s);
+        case 64: return launch_mlp_h64(mode, a, grid, s);
+        case 128: return launch_mlp_h128(mode, a, grid, s);
+        case 256: return launch_mlp_h256(mode, a, grid, s);
+    }
+    return cudaErrorInvalidValue;
+}
+int occupancy_any(int H, int mode, int YR) {
+    switch (H) {
+        case 32: return occupancy_mlp_h32(mode, YR);
+        case 64: return occupancy_mlp_h64(mode, YR);
+        case 128: return occupancy_mlp_h128(mode, YR);
+        case 256: return occupancy_mlp_h256(mode, YR);
+    }
+    return 0;
+}
+
+template <typename T>
+int dalloc(mjb_engine* e, T** p, size_t n) {
+    CK(e, cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T)));
+    CK(e, cudaMemsetAsync(*p, 0, std::max<size_t>(n, 1) * sizeof(T), e->stream));
+    return 0;
+}
+
+int allreduce(mjb_engine* e, void* buf, size_t count, ncclDataType_t dt, ncclRedOp_t op = ncclSum) {
+    if (!e->comm) return 0;
+    NK(e, g_nccl.AllReduce(buf, buf, count, dt, op, e->comm, e->stream));
+    return 0;
+}
+
+int set_params(mjb_engine* e, ParamSet& ps, const float* theta_src) {
+    if (theta_src) CK(e, cudaMemcpyAsync(ps.theta, theta_src, sizeof(float) * e->d, cudaMemcpyDefault, e->stream));
+    launch_clamp_tail(ps.theta, e->d, e->A, e->cfg.min_log_std, e->stream);
+    if (e->linear) launch_prep_linear(ps.theta, e->LL, ps.prep, e->stream);
+    else launch_prep_mlp(ps.theta, e->PL, ps.prep, e->stream);
+    e->launches += 2;
+    CK(e, cudaGetLastError());
+    return 0;
+}
+
+int ensure_idx(mjb_engine* e, long long n) {
+    if (n <= e->idx_cap) return 0;
+    if (e->idx_dev) cudaFree(e->idx_dev);
+    e->idx_cap = n;
+    CK(e, cudaMalloc(&e->idx_dev, sizeof(int) * n));
+    return 0;
+}
+
+// Launch one policy tile kernel over rows [0, n).
+int run_policy(mjb_engine* e, int mode, const ParamSet& ps, const float* tangent_prep, long long n,
+               const int* idx, const float* weight, int old_flags) {
+    const bool bwd = (mode == MODE_VPG || mode == MODE_FVP);
+    if (e->occ[mode] == 0) {
+        e->occ[mode] = e->linear ? 2 : occupancy_any(e->H, mode, e->PL.YR);
+        if (e->occ[mode] <= 0) FAIL(e, "kernel does not fit on this device (occupancy 0)");
+    }
+    const int MT = e->linear ? 128 : mlp_tile_rows_for(e->H);
+    const long long tiles = (n + MT - 1) / MT;
+    int grid = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)e->occ[mode] * e->num_sms));
+    grid = std::min(grid, e->max_grid);
+    if (bwd) CK(e, cudaMemsetAsync(e->gpartial, 0, sizeof(float) * (size_t)grid * e->gstride, e->stream));
+    cudaError_t ce;
+    if (e->linear) {
+        LinArgs a;
+        a.L = e->LL; a.P = ps.prep; a.T = tangent_prep;
+        a.in_shift = ps.in_shift; a.in_scale = ps.in_scale; a.out_shift = ps.out_shift; a.out_scale = ps.out_scale;
+        a.obs = e->obs; a.act = e->act; a.idx = idx; a.n = n; a.weight = weight;
+        a.ll_old = e->ll_old; a.mu_old = e->mu_old; a.old_log_std = e->pold.prep + e->LL.oLS; a.old_flags = old_flags;
+        a.eval_partial = e->eval_partial; a.gpartial = e->gpartial; a.gstride = e->gstride;
+        ce = launch_linear(mode, a, grid, e->stream);
+    } else {
+        MlpArgs a;
+        memset(&a, 0, sizeof(a));
+        a.L = e->PL; a.P = ps.prep; a.T = tangent_prep;
+        a.in_shift = ps.in_shift; a.in_scale = ps.in_scale; a.out_shift = ps.out_shift; a.out_scale = ps.out_scale;
+        a.obs = e->obs; a.obs_dim = e->cfg.obs_dim; a.act = e->act; a.idx = idx; a.n = n; a.weight = weight;
+        a.ll_old = e->ll_old; a.mu_old = e->mu_old; a.old_log_std = e->pold.prep + e->PL.oLS; a.old_flags = old_flags;
+        a.eval_partial = e->eval_partial; a.gpartial = e->gpartial; a.gstride = e->gstride;
+        ce = launch_mlp_any(e->H, mode, a, grid, e->stream);
+    }
+    if (ce != cudaSuccess) FAIL(e, std::string("policy kernel launch: ") + cudaGetErrorString(ce));
+    e->launches += 1;
+    return grid;
+}
+
+// Make ll_old / mu_old valid for `rows` rows (forward with the OLD parameters and transforms).
+int ensure_old_cache(mjb_engine* e, long long rows) {
+    if (e->old_cache_valid && e->cache_rows >= rows) return 0;
+    int g = run_policy(e, MODE_EVAL, e->pold, nullptr, rows, nullptr, nullptr, OLD_WRITE);
+    if (g < 0) return -1;
+    e->old_cache_valid = true;
+    e->cache_rows = rows;
+    return 0;
+}
+
+// F v (undamped, all-reduced) into out.  v, out: device pointers of d floats.
+int fvp_device(mjb_engine* e, const float* v, const int* idx, long long n_idx, float* out) {
+    if (e->linear) launch_prep_linear(v, e->LL, e->prep_tan, e->stream);
+    else launch_prep_mlp(v, e->PL, e->prep_tan, e->stream);
+    e->launches += 1;
+    const long long n = idx ? n_idx : e->n_roll;
+    cudaEventRecord(e->ev[4], e->stream);
+    int grid = run_policy(e, MODE_FVP, e->pnew, e->prep_tan, n, idx, nullptr, 0);
+    if (grid < 0) return -1;
+    cudaEventRecord(e->ev[5], e->stream);
+    launch_reduce_partials(e->gpartial, grid, e->gstride, e->d, e->dsc + (idx ? DS_SCALE_SUB : DS_SCALE), out,
+                           e->pnew.theta, v, e->tLS, 1, e->stream);
+    e->launches += 1;
+    CK(e, cudaGetLastError());
+    return allreduce(e, out, e->d, ncclFloat);
+}
+
+int set_subsample_scale(mjb_engine* e, long long n_idx_local) {
+    e->h_dsc[DS_CNT] = (double)n_idx_local;
+    CK(e, cudaMemcpyAsync(e->dsc + DS_CNT, e->h_dsc + DS_CNT, sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    if (allreduce(e, e->dsc + DS_CNT, 1, ncclDouble)) return -1;
+    CK(e, cudaMemcpyAsync(e->h_dsc + DS_CNT, e->dsc + DS_CNT, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    e->h_dsc[DS_SCALE_SUB] = 1.0 / e->h_dsc[DS_CNT];
+    e->h_dsc[DS_SCALE_SUB + 1] = 1.0 / (double)e->cfg.world_size;
+    CK(e, cudaMemcpyAsync(e->dsc + DS_SCALE_SUB, e->h_dsc + DS_SCALE_SUB, 2 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    return 0;
+}
+
+int eval_device(mjb_engine* e, double out[2]) {
+    if (!e->have_white) FAIL(e, "mjb_policy_eval: call mjb_process_paths first");
+    if (ensure_old_cache(e, e->n_roll)) return -1;
+    int grid = run_policy(e, MODE_EVAL, e->pnew, nullptr, e->n_roll, nullptr, e->adv_white, OLD_READ);
+    if (grid < 0) return -1;
+    launch_reduce_eval(e->eval_partial, grid, e->dsc + DS_EVAL, e->stream);
+    e->launches += 1;
+    if (allreduce(e, e->dsc + DS_EVAL, 2, ncclDouble)) return -1;
+    CK(e, cudaMemcpyAsync(e->h_dsc + DS_EVAL, e->dsc + DS_EVAL, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    // torch.mean in fp32: round the mean to fp32 like the reference's scalar
+    out[0] = (double)(float)(e->h_dsc[DS_EVAL] / (double)e->n_glob_roll);
+    out[1] = (double)(float)(e->h_dsc[DS_EVAL + 1] / (double)e->n_glob_roll);
+    return 0;
+}
+
+// VPG into e->g (all-reduced).  Returns surr_before through *surr when non-null.
+int vpg_device(mjb_engine* e, int include_demo, double demo_lam, double* surr) {
+    if (!e->have_white) FAIL(e, "mjb_policy_vpg: call mjb_process_paths first");
+    long long n = e->n_roll;
+    const float* w = e->adv_white;
+    if (include_demo && e->n_demo > 0) {
+        launch_dapg_weights(e->adv, e->n_roll, e->n_demo, e->dsc + DS_STATS, demo_lam, e->weights, e->stream);
+        e->launches += 1;
+        n = e->n_roll + e->n_demo;
+        w = e->weights;
+    }
+    int flags;
+    if (e->old_equals_new) {
+        flags = OLD_WRITE;                 // LR == 1 exactly; cache mu/LL of the old policy on the way
+    } else {
+        if (ensure_old_cache(e, n)) return -1;
+        flags = OLD_READ;
+    }
+    int grid = run_policy(e, MODE_VPG, e->pnew, nullptr, n, nullptr, w, flags);
+    if (grid < 0) return -1;
+    if (flags == OLD_WRITE) { e->old_cache_valid = true; e->cache_rows = n; }
+    launch_reduce_partials(e->gpartial, grid, e->gstride, e->d, e->dsc + DS_SCALE, e->g, nullptr, nullptr, e->tLS, 0, e->stream);
+    e->launches += 1;
+    if (allreduce(e, e->g, e->d, ncclFloat)) return -1;
+    if (surr) {
+        if (n == e->n_roll) {
+            launch_reduce_eval(e->eval_partial, grid, e->dsc + DS_EVAL, e->stream);
+            e->launches += 1;
+            if (allreduce(e, e->dsc + DS_EVAL, 2, ncclDouble)) return -1;
+            CK(e, cudaMemcpyAsync(e->h_dsc + DS_EVAL, e->dsc + DS_EVAL, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+            CK(e, cudaStreamSynchronize(e->stream));
+            *surr = (double)(float)(e->h_dsc[DS_EVAL] / (double)e->n_glob_roll);
+        } else {
+            double o[2];
+            if (eval_device(e, o)) return -1;
+            *surr = o[0];
+        }
+    }
+    CK(e, cudaGetLastError());
+    return 0;
+}
+
+int cg_device(mjb_engine* e, const float* b, int iters, float damping, float tol, const int* idx_dev, long long n_idx) {
+    launch_cg_init(b, e->x, e->r, e->p, e->d, e->dsc + DS_CG, e->stream);
+    e->launches += 1;
+    for (int i = 0; i < iters; ++i) {
+        const int* idx = idx_dev ? idx_dev + (size_t)i * n_idx : nullptr;
+        if (fvp_device(e, e->p, idx, n_idx, e->Fp)) return -1;
+        launch_cg_update(e->Fp, damping, tol, e->x, e->r, e->p, e->d, e->dsc + DS_CG, e->stream);
+        e->launches += 1;
+    }
+    CK(e, cudaGetLastError());
+    return 0;
+}
+
+int upload_idx(mjb_engine* e, const int32_t* idx, long long total) {
+    if (ensure_idx(e, total)) return -1;
+    CK(e, cudaMemcpyAsync(e->idx_dev, idx, sizeof(int) * total, cudaMemcpyDefault, e->stream));
+    return 0;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int mjb_version(void) { return MJB_VERSION; }
+
+const char* mjb_last_error(const mjb_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+void mjb_destroy(mjb_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->comm) g_nccl.CommDestroy(e->comm);
+    void* bufs[] = {e->pnew.theta, e->pnew.prep, e->pnew.in_shift, e->pnew.in_scale, e->pnew.out_shift, e->pnew.out_scale,
+                    e->pold.theta, e->pold.prep, e->pold.in_shift, e->pold.in_scale, e->pold.out_shift, e->pold.out_scale,
+                    e->prep_tan, e->obs, e->act, e->rew, e->path_off, e->term, e->tstep, e->ret, e->adv, e->base,
+                    e->adv_white, e->weights, e->path_ret, e->ll_old, e->mu_old, e->gpartial, e->eval_partial,
+                    e->mom_scratch, e->dsc, e->g, e->x, e->r, e->p, e->Fp, e->tmpv, e->idx_dev, e->stage64, e->vf_w,
+                    e->vf_m, e->vf_v, e->vf_wT, e->vf_prep, e->perm_dev, e->fit_obs, e->fit_tstep, e->fit_ret};
+    for (void* b : bufs) if (b) cudaFree(b);
+    if (e->pinned) cudaFreeHost(e->pinned);
+    if (e->h_dsc) cudaFreeHost(e->h_dsc);
+    for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int mjb_create(const mjb_config* cfg, mjb_engine** out) {
+    if (!cfg || !out) { g_create_error = "null argument"; return -1; }
+    *out = nullptr;
+    mjb_engine* e = new mjb_engine();
+    e->cfg = *cfg;
+    for (auto& ev : e->ev) ev = nullptr;
+    auto fail = [&](const std::string& m) { g_create_error = m.empty() ? e->err : m; mjb_destroy(e); return -1; };
+    if (cfg->obs_dim < 1 || cfg->act_dim < 1 || cfg->act_dim > 32) return fail("act_dim must be in [1,32], obs_dim >= 1");
+    if (cfg->n_hidden != 0 && cfg->n_hidden != 2) return fail("only 0 (linear) or 2 hidden layers are supported");
+    if (cfg->max_samples < 1 || cfg->max_paths < 1) return fail("max_samples/max_paths must be positive");
+    if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) return fail("bad world_size/rank");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail("no CUDA device (this engine has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail("bad device ordinal");
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return fail("cudaSetDevice failed");
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, cfg->device);
+    if (prop.major < 10) return fail("mjrl_b200 kernels are built for sm_100a (Blackwell) only");
+    e->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("stream create failed");
+    for (auto& ev : e->ev) if (cudaEventCreate(&ev) != cudaSuccess) return fail("event create failed");
+
+    e->linear = cfg->n_hidden == 0;
+    e->A = cfg->act_dim;
+    if (e->linear) {
+        e->LL = make_lin_layout(cfg->obs_dim, cfg->act_dim);
+        e->d = e->LL.d; e->prep_total = e->LL.total; e->tLS = e->LL.tLS;
+    } else {
+        if (cfg->hidden[0] < 1 || cfg->hidden[1] < 1 || cfg->hidden[0] > 256 || cfg->hidden[1] > 256)
+            return fail("hidden sizes must be in [1,256]");
+        e->H = pad_hidden(std::max(cfg->hidden[0], cfg->hidden[1]));
+        e->PL = make_prep_layout(e->H, cfg->obs_dim, cfg->act_dim, cfg->hidden[0], cfg->hidden[1], true);
+        e->d = e->PL.d; e->prep_total = e->PL.total; e->tLS = e->PL.tLS;
+    }
+    const int vh0 = cfg->vf_hidden[0] > 0 ? cfg->vf_hidden[0] : 128, vh1 = cfg->vf_hidden[1] > 0 ? cfg->vf_hidden[1] : 128;
+    if (vh0 > 256 || vh1 > 256 || vh0 % 4 || vh1 % 4) return fail("vf hidden sizes must be multiples of 4, <= 256");
+    e->cfg.vf_hidden[0] = vh0; e->cfg.vf_hidden[1] = vh1;
+    e->vfH = pad_hidden(std::max(vh0, vh1));
+    e->VPL = make_prep_layout(e->vfH, cfg->obs_dim + 4, 1, vh0, vh1, false);
+    e->vf_d = e->VPL.d;
+
+    e->cap = cfg->max_samples;
+    const size_t N = (size_t)e->cap, O = cfg->obs_dim, A = cfg->act_dim;
+#define ALLOC(ptr, n) if (dalloc(e, &(ptr), (n))) return fail("")
+    for (ParamSet* ps : {&e->pnew, &e->pold}) {
+        ALLOC(ps->theta, e->d); ALLOC(ps->prep, e->prep_total);
+        ALLOC(ps->in_shift, O); ALLOC(ps->in_scale, O); ALLOC(ps->out_shift, A); ALLOC(ps->out_scale, A);
+        std::vector<float> ones(std::max(O, A), 1.0f);
+        cudaMemcpyAsync(ps->in_scale, ones.data(), O * sizeof(float), cudaMemcpyHostToDevice, e->stream);
+        cudaMemcpyAsync(ps->out_scale, ones.data(), A * sizeof(float), cudaMemcpyHostToDevice, e->stream);
+        cudaStreamSynchronize(e->stream);
+    }
+    ALLOC(e->prep_tan, e->prep_total);
+    ALLOC(e->obs, N * O); ALLOC(e->act, N * A); ALLOC(e->rew, N);
+    ALLOC(e->path_off, (size_t)cfg->max_paths + 2); ALLOC(e->term, (size_t)cfg->max_paths + 1); ALLOC(e->tstep, N);
+    ALLOC(e->ret, N); ALLOC(e->adv, N); ALLOC(e->base, N); ALLOC(e->adv_white, N); ALLOC(e->weights, N);
+    ALLOC(e->path_ret, (size_t)cfg->max_paths + 1);
+    ALLOC(e->ll_old, N); ALLOC(e->mu_old, N * A);
+    e->max_grid = 2 * e->num_sms;
+    e->gstride = round_up(e->d, 32);
+    ALLOC(e->gpartial, (size_t)e->max_grid * e->gstride);
+    ALLOC(e->eval_partial, (size_t)2 * e->max_grid);
+    ALLOC(e->mom_scratch, 2 * 512);
+    ALLOC(e->dsc, DS_TOTAL);
+    if (cudaMallocHost(reinterpret_cast<void**>(&e->h_dsc), DS_TOTAL * sizeof(double)) != cudaSuccess) return fail("pinned alloc failed");
+    memset(e->h_dsc, 0, DS_TOTAL * sizeof(double));
+    ALLOC(e->g, e->d); ALLOC(e->x, e->d); ALLOC(e->r, e->d); ALLOC(e->p, e->d); ALLOC(e->Fp, e->d); ALLOC(e->tmpv, e->d);
+    e->stage64_elems = N * std::max(O, A);
+    ALLOC(e->stage64, e->stage64_elems);
+    ALLOC(e->vf_w, e->vf_d); ALLOC(e->vf_m, e->vf_d); ALLOC(e->vf_v, e->vf_d);
+    ALLOC(e->vf_wT, (size_t)(O + 4) * vh0 + (size_t)vh0 * vh1);
+    ALLOC(e->vf_prep, e->VPL.total);
+#undef ALLOC
+    e->pinned_bytes = std::min<size_t>(N * std::max(O, A) * sizeof(double), (size_t)64 << 20);
+    e->pinned_bytes = std::max<size_t>(e->pinned_bytes, (size_t)1 << 20);
+    if (cudaMallocHost(&e->pinned, 2 * e->pinned_bytes) != cudaSuccess) return fail("pinned staging alloc failed");
+    e->h_dsc[DS_SCALE + 1] = 1.0 / (double)cfg->world_size;
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess) return fail("init sync failed");
+    *out = e;
+    return 0;
+}
+
+int mjb_synchronize(mjb_engine* e) { CK(e, cudaStreamSynchronize(e->stream)); return 0; }
+
+int mjb_comm_unique_id(void* id128) {
+    std::string err;
+    if (!g_nccl.load(err)) { g_create_error = err; return -1; }
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return -1; }
+    memcpy(id128, &id, sizeof(id));
+    return 0;
+}
+
+int mjb_comm_init(mjb_engine* e, const void* id128) {
+    if (e->cfg.world_size == 1) return 0;
+    if (!g_nccl.load(e->err)) return -1;
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    CK(e, cudaSetDevice(e->cfg.device));
+    NK(e, g_nccl.CommInitRank(&e->comm, e->cfg.world_size, id, e->cfg.rank));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- batch
+static int finish_upload(mjb_engine* e, int which, int n_paths, const int32_t* len, const uint8_t* terminated, long long n) {
+    if (which == MJB_BATCH_ROLLOUT) {
+        e->h_path_off.assign((size_t)n_paths + 1, 0);
+        for (int i = 0; i < n_paths; ++i) e->h_path_off[i + 1] = e->h_path_off[i] + len[i];
+        CK(e, cudaMemcpyAsync(e->path_off, e->h_path_off.data(), sizeof(int) * (n_paths + 1), cudaMemcpyHostToDevice, e->stream));
+        std::vector<unsigned char> t(n_paths, 0);
+        if (terminated) memcpy(t.data(), terminated, n_paths);
+        CK(e, cudaMemcpyAsync(e->term, t.data(), n_paths, cudaMemcpyHostToDevice, e->stream));
+        launch_tstep(e->path_off, n_paths, e->tstep, e->stream);
+        e->launches += 1;
+        e->n_roll = n; e->n_paths = n_paths; e->n_demo = 0;
+        e->have_adv = e->have_white = false;
+        // global sample / path counts
+        e->h_dsc[DS_CNT] = (double)n; e->h_dsc[DS_CNT + 1] = (double)n_paths;
+        CK(e, cudaMemcpyAsync(e->dsc + DS_CNT, e->h_dsc + DS_CNT, 2 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        if (allreduce(e, e->dsc + DS_CNT, 2, ncclDouble)) return -1;
+        CK(e, cudaMemcpyAsync(e->h_dsc + DS_CNT, e->dsc + DS_CNT, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));     // also keeps the host vectors above alive long enough
+        e->n_glob_roll = (long long)e->h_dsc[DS_CNT];
+        e->n_glob_paths = (int)e->h_dsc[DS_CNT + 1];
+        e->h_dsc[DS_SCALE] = 1.0 / (double)e->n_glob_roll;
+        e->h_dsc[DS_SCALE + 1] = 1.0 / (double)e->cfg.world_size;
+        CK(e, cudaMemcpyAsync(e->dsc + DS_SCALE, e->h_dsc + DS_SCALE, 2 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    } else {
+        e->n_demo = n;
+    }
+    e->old_cache_valid = false;
+    return 0;
+}
+
+int mjb_batch_upload(mjb_engine* e, int which, int32_t n_paths, const double* const* obs, const double* const* act,
+                     const double* const* rew, const int32_t* len, const uint8_t* terminated) {
+    if (which != MJB_BATCH_ROLLOUT && which != MJB_BATCH_DEMO) FAIL(e, "bad batch id");
+    if (n_paths < 0 || (which == MJB_BATCH_ROLLOUT && n_paths > e->cfg.max_paths)) FAIL(e, "too many paths for max_paths");
+    long long n = 0;
+    for (int i = 0; i < n_paths; ++i) { if (len[i] < 0) FAIL(e, "negative path length"); n += len[i]; }
+    const long long row0 = which == MJB_BATCH_DEMO ? e->n_roll : 0;
+    if (row0 + n > e->cap) FAIL(e, "batch exceeds max_samples");
+    CK(e, cudaSetDevice(e->cfg.device));
+    // stream each field through the double-buffered pinned ring: host memcpy of chunk k overlaps the DMA of k-1
+    struct Field { const double* const* src; int width; int kind; };
+    const Field fields[3] = {{obs, e->cfg.obs_dim, 0}, {act, e->cfg.act_dim, 1}, {rew, 1, 2}};
+    cudaEvent_t done[2] = {e->ev[0], e->ev[1]};
+    int slot = 0, used[2] = {0, 0};
+    for (const Field& f : fields) {
+        if (!f.src) continue;
+        if (f.kind == 2 && which == MJB_BATCH_DEMO) continue;
+        const size_t cap_el = e->pinned_bytes / sizeof(double);
+        double* dst_dev = (f.kind == 2) ? e->rew : e->stage64;
+        size_t dev_off = 0;
+        int pi = 0; size_t in_path = 0;
+        while (pi < n_paths) {
+            if (used[slot]) CK(e, cudaEventSynchronize(done[slot]));
+            double* pin = reinterpret_cast<double*>(static_cast<char*>(e->pinned) + slot * e->pinned_bytes);
+            size_t fill = 0;
+            while (pi < n_paths && fill < cap_el) {
+                const size_t total = (size_t)len[pi] * f.width;
+                const size_t take = std::min(total - in_path, cap_el - fill);
+                memcpy(pin + fill, f.src[pi] + in_path, take * sizeof(double));
+                fill += take; in_path += take;
+                if (in_path == total) { ++pi; in_path = 0; }
+            }
+            CK(e, cudaMemcpyAsync(dst_dev + dev_off, pin, fill * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+            CK(e, cudaEventRecord(done[slot], e->stream));
+            used[slot] = 1;
+            dev_off += fill;
+            slot ^= 1;
+        }
+        if (f.kind == 0) launch_f64_to_f32(e->stage64, e->obs + (size_t)row0 * e->cfg.obs_dim, n * e->cfg.obs_dim, e->stream);
+        if (f.kind == 1) launch_f64_to_f32(e->stage64, e->act + (size_t)row0 * e->cfg.act_dim, n * e->cfg.act_dim, e->stream);
+        e->launches += (f.kind != 2);
+    }
+    return finish_upload(e, which, n_paths, len, terminated, n);
+}
+
+int mjb_batch_upload_flat(mjb_engine* e, int which, int32_t n_paths, const double* obs, const double* act,
+                          const double* rew, const int32_t* len, const uint8_t* terminated) {
+    if (which != MJB_BATCH_ROLLOUT && which != MJB_BATCH_DEMO) FAIL(e, "bad batch id");
+    if (n_paths < 0 || (which == MJB_BATCH_ROLLOUT && n_paths > e->cfg.max_paths)) FAIL(e, "too many paths for max_paths");
+    long long n = 0;
+    for (int i = 0; i < n_paths; ++i) n += len[i];
+    const long long row0 = which == MJB_BATCH_DEMO ? e->n_roll : 0;
+    if (row0 + n > e->cap) FAIL(e, "batch exceeds max_samples");
+    CK(e, cudaSetDevice(e->cfg.device));
+    CK(e, cudaMemcpyAsync(e->stage64, obs, sizeof(double) * n * e->cfg.obs_dim, cudaMemcpyDefault, e->stream));
+    launch_f64_to_f32(e->stage64, e->obs + (size_t)row0 * e->cfg.obs_dim, n * e->cfg.obs_dim, e->stream);
+    CK(e, cudaMemcpyAsync(e->stage64, act, sizeof(double) * n * e->cfg.act_dim, cudaMemcpyDefault, e->stream));
+    launch_f64_to_f32(e->stage64, e->act + (size_t)row0 * e->cfg.act_dim, n * e->cfg.act_dim, e->stream);
+    if (rew && which == MJB_BATCH_ROLLOUT) CK(e, cudaMemcpyAsync(e->rew, rew, sizeof(double) * n, cudaMemcpyDefault, e->stream));
+    e->launches += 2;
+    return finish_upload(e, which, n_paths, len, terminated, n);
+}
+
+int mjb_batch_set_advantages(mjb_engine* e, const double* adv_concat) {
+    CK(e, cudaMemcpyAsync(e->adv, adv_concat, sizeof(double) * e->n_roll, cudaMemcpyDefault, e->stream));
+    e->have_adv = true; e->have_white = false;
+    return 0;
+}
+
+int64_t mjb_batch_size(const mjb_engine* e, int which) { return which == MJB_BATCH_DEMO ? e->n_demo : e->n_roll; }
+
+// ------------------------------------------------------------------------------- returns / advantages
+int mjb_compute_returns(mjb_engine* e, double gamma) {
+    launch_returns(e->rew, e->path_off, e->n_paths, gamma, e->ret, e->path_ret, e->stream);
+    e->launches += 1;
+    CK(e, cudaGetLastError());
+    return 0;
+}
+
+int mjb_vf_predict(mjb_engine* e) {
+    if (e->occ[MODE_VF] == 0) {
+        e->occ[MODE_VF] = occupancy_any(e->vfH, MODE_VF, e->VPL.YR);
+        if (e->occ[MODE_VF] <= 0) FAIL(e, "vf kernel does not fit");
+    }
+    const int MT = mlp_tile_rows_for(e->vfH);
+    const long long tiles = (e->n_roll + MT - 1) / MT;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)e->occ[MODE_VF] * e->num_sms));
+    MlpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.L = e->VPL; a.P = e->vf_prep; a.obs = e->obs; a.obs_dim = e->cfg.obs_dim; a.tstep = e->tstep; a.n = e->n_roll;
+    a.vf_out = e->base;
+    cudaError_t ce = launch_mlp_any(e->vfH, MODE_VF, a, grid, e->stream);
+    if (ce != cudaSuccess) FAIL(e, std::string("vf predict launch: ") + cudaGetErrorString(ce));
+    e->launches += 1;
+    return 0;
+}
+
+int mjb_compute_advantages(mjb_engine* e, double gamma, double gae_lambda, int use_gae) {
+    launch_advantages(e->rew, e->base, e->ret, e->path_off, e->term, e->n_paths, gamma, gamma * gae_lambda, use_gae,
+                      e->adv, e->stream);
+    e->launches += 1;
+    e->have_adv = true; e->have_white = false;
+    CK(e, cudaGetLastError());
+    return 0;
+}
+
+static int d2any(mjb_engine* e, void* dst, const void* src, size_t bytes) {
+    CK(e, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+int mjb_get_returns(mjb_engine* e, double* out) { return d2any(e, out, e->ret, sizeof(double) * e->n_roll); }
+int mjb_get_baseline(mjb_engine* e, float* out) { return d2any(e, out, e->base, sizeof(float) * e->n_roll); }
+int mjb_get_advantages(mjb_engine* e, double* out) { return d2any(e, out, e->adv, sizeof(double) * e->n_roll); }
+int mjb_get_adv_white(mjb_engine* e, float* out) { return d2any(e, out, e->adv_white, sizeof(float) * e->n_roll); }
+
+int mjb_process_paths(mjb_engine* e, mjb_batch_stats* out) {
+    if (!e->have_adv) FAIL(e, "mjb_process_paths: advantages not set");
+    // mean, then population variance about the mean (two passes, like numpy's std)
+    launch_moments(e->adv, e->n_roll, nullptr, e->mom_scratch, e->dsc + DS_MOM, e->stream);
+    if (allreduce(e, e->dsc + DS_MOM, 2, ncclDouble)) return -1;
+    CK(e, cudaMemcpyAsync(e->h_dsc + DS_MOM, e->dsc + DS_MOM, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    const double mean = e->h_dsc[DS_MOM] / (double)e->n_glob_roll;
+    e->h_dsc[DS_STATS] = mean;
+    CK(e, cudaMemcpyAsync(e->dsc + DS_STATS, e->h_dsc + DS_STATS, sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    launch_moments(e->adv, e->n_roll, e->dsc + DS_STATS, e->mom_scratch, e->dsc + DS_MOM, e->stream);
+    if (allreduce(e, e->dsc + DS_MOM, 2, ncclDouble)) return -1;
+    CK(e, cudaMemcpyAsync(e->h_dsc + DS_MOM, e->dsc + DS_MOM, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    const double sd = std::sqrt(e->h_dsc[DS_MOM + 1] / (double)e->n_glob_roll);
+    e->h_dsc[DS_STATS + 1] = sd;
+    CK(e, cudaMemcpyAsync(e->dsc + DS_STATS, e->h_dsc + DS_STATS, 2 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    launch_whiten(e->adv, e->n_roll, e->dsc + DS_STATS, e->adv_white, e->stream);
+    e->launches += 5;
+    e->have_white = true;
+    // path-return statistics (batch_reinforce.py:188-192)
+    std::vector<double> pr((size_t)std::max(1, e->n_paths));
+    CK(e, cudaMemcpyAsync(pr.data(), e->path_ret, sizeof(double) * e->n_paths, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    double s = 0, mn = INFINITY, mx = -INFINITY;
+    for (int i = 0; i < e->n_paths; ++i) { s += pr[i]; mn = std::min(mn, pr[i]); mx = std::max(mx, pr[i]); }
+    double* h = e->h_dsc + DS_RET;
+    h[0] = s; h[1] = -mn; h[2] = mx;
+    if (e->comm) {
+        CK(e, cudaMemcpyAsync(e->dsc + DS_RET, h, 3 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        if (allreduce(e, e->dsc + DS_RET, 1, ncclDouble, ncclSum)) return -1;
+        if (allreduce(e, e->dsc + DS_RET + 1, 2, ncclDouble, ncclMax)) return -1;
+        CK(e, cudaMemcpyAsync(h, e->dsc + DS_RET, 3 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));
+    }
+    const double rmean = h[0] / (double)e->n_glob_paths;
+    double ss = 0;
+    for (int i = 0; i < e->n_paths; ++i) ss += (pr[i] - rmean) * (pr[i] - rmean);
+    h[3] = ss;
+    if (e->comm) {
+        CK(e, cudaMemcpyAsync(e->dsc + DS_RET + 3, h + 3, sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        if (allreduce(e, e->dsc + DS_RET + 3, 1, ncclDouble)) return -1;
+        CK(e, cudaMemcpyAsync(h + 3, e->dsc + DS_RET + 3, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));
+    }
+    if (out) {
+        out->mean_return = rmean; out->std_return = std::sqrt(h[3] / (double)e->n_glob_paths);
+        out->min_return = -h[1]; out->max_return = h[2];
+        out->adv_mean = mean; out->adv_std = sd; out->n_samples_global = e->n_glob_roll;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ policy
+int mjb_policy_dim(const mjb_engine* e) { return e->d; }
+
+int mjb_policy_set_params(mjb_engine* e, const float* theta, int set_new, int set_old) {
+    if (set_new && set_params(e, e->pnew, theta)) return -1;
+    if (set_old && set_params(e, e->pold, theta)) return -1;
+    if (set_new && set_old) e->old_equals_new = e->transforms_equal;
+    else if (set_new || set_old) e->old_equals_new = false;
+    if (set_old) e->old_cache_valid = false;
+    return 0;
+}
+
+int mjb_policy_get_params(mjb_engine* e, float* theta_out, int which_old) {
+    return d2any(e, theta_out, which_old ? e->pold.theta : e->pnew.theta, sizeof(float) * e->d);
+}
+
+int mjb_policy_set_transforms(mjb_engine* e, const float* in_shift, const float* in_scale, const float* out_shift,
+                              const float* out_scale, int which_old) {
+    ParamSet& ps = which_old ? e->pold : e->pnew;
+    const size_t O = e->cfg.obs_dim, A = e->cfg.act_dim;
+    if (in_shift) CK(e, cudaMemcpyAsync(ps.in_shift, in_shift, O * sizeof(float), cudaMemcpyDefault, e->stream));
+    if (in_scale) CK(e, cudaMemcpyAsync(ps.in_scale, in_scale, O * sizeof(float), cudaMemcpyDefault, e->stream));
+    if (out_shift) CK(e, cudaMemcpyAsync(ps.out_shift, out_shift, A * sizeof(float), cudaMemcpyDefault, e->stream));
+    if (out_scale) CK(e, cudaMemcpyAsync(ps.out_scale, out_scale, A * sizeof(float), cudaMemcpyDefault, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    e->transforms_equal = false;       // conservative: the reference updates only policy.model (A10)
+    e->old_equals_new = false;
+    if (which_old) e->old_cache_valid = false;
+    return 0;
+}
+
+int mjb_policy_eval(mjb_engine* e, double out[2]) { return eval_device(e, out); }
+
+int mjb_policy_vpg(mjb_engine* e, int include_demo, double demo_lam, float* g_out) {
+    if (vpg_device(e, include_demo, demo_lam, nullptr)) return -1;
+    if (g_out) return d2any(e, g_out, e->g, sizeof(float) * e->d);
+    return 0;
+}
+
+int mjb_policy_fvp(mjb_engine* e, const float* v, float damping, const int32_t* idx, int64_t n_idx, float* out) {
+    CK(e, cudaMemcpyAsync(e->tmpv, v, sizeof(float) * e->d, cudaMemcpyDefault, e->stream));
+    const int* idx_dev = nullptr;
+    if (idx) {
+        if (upload_idx(e, idx, n_idx)) return -1;
+        if (set_subsample_scale(e, n_idx)) return -1;
+        idx_dev = e->idx_dev;
+    }
+    if (fvp_device(e, e->tmpv, idx_dev, n_idx, e->Fp)) return -1;
+    // + damping * v  (npg_cg.py:81)
+    e->h_dsc[DS_ALPHA] = (double)damping;
+    CK(e, cudaMemcpyAsync(e->dsc + DS_ALPHA, e->h_dsc + DS_ALPHA, sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    launch_axpy_clamp(e->Fp, e->tmpv, e->dsc + DS_ALPHA, 1.0, e->d, 0, 0.0f, e->Fp, e->stream);
+    e->launches += 1;
+    cudaEventSynchronize(e->ev[5]);
+    cudaEventElapsedTime(&e->last_fvp_ms, e->ev[4], e->ev[5]);
+    return d2any(e, out, e->Fp, sizeof(float) * e->d);
+}
+
+int mjb_policy_cg(mjb_engine* e, const float* b, int iters, float damping, float residual_tol, const int32_t* idx,
+                  int64_t n_idx, float* x_out) {
+    if (b) CK(e, cudaMemcpyAsync(e->g, b, sizeof(float) * e->d, cudaMemcpyDefault, e->stream));
+    const int* idx_dev = nullptr;
+    if (idx) {
+        if (upload_idx(e, idx, (long long)iters * n_idx)) return -1;
+        if (set_subsample_scale(e, n_idx)) return -1;
+        idx_dev = e->idx_dev;
+    }
+    if (cg_device(e, e->g, iters, damping, residual_tol, idx_dev, n_idx)) return -1;
+    if (x_out) return d2any(e, x_out, e->x, sizeof(float) * e->d);
+    return 0;
+}
+
+int mjb_policy_step(mjb_engine* e, int algo, double step_size_or_kl, double const_learn_rate, int cg_iters,
+                    float damping, double demo_lam, const int32_t* hvp_idx, int64_t n_idx, mjb_step_stats* out) {
+    if (algo < MJB_ALGO_NPG || algo > MJB_ALGO_DAPG) FAIL(e, "bad algo");
+    mjb_step_stats st;
+    memset(&st, 0, sizeof(st));
+    CK(e, cudaEventRecord(e->ev[0], e->stream));
+    if (vpg_device(e, algo == MJB_ALGO_DAPG, demo_lam, &st.surr_before)) return -1;
+    CK(e, cudaEventRecord(e->ev[1], e->stream));
+    const int* idx_dev = nullptr;
+    if (hvp_idx) {
+        if (upload_idx(e, hvp_idx, (long long)cg_iters * n_idx)) return -1;
+        if (set_subsample_scale(e, n_idx)) return -1;
+        idx_dev = e->idx_dev;
+    }
+    if (cg_device(e, e->g, cg_iters, damping, 1e-10f, idx_dev, n_idx)) return -1;
+    launch_dot(e->g, e->x, e->d, e->dsc + DS_DOT, e->stream);
+    e->launches += 1;
+    CK(e, cudaEventRecord(e->ev[2], e->stream));
+    CK(e, cudaMemcpyAsync(e->h_dsc + DS_CG, e->dsc + DS_CG, 8 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    st.cg_iters_run = (int)e->h_dsc[DS_CG + 2];
+    const float gx = (float)e->h_dsc[DS_DOT];
+    st.vpg_dot_npg = gx;
+    // step size in the reference's fp32 scalar arithmetic (npg_cg.py:128-133, trpo.py:102-103, dapg.py:111-112)
+    float alpha;
+    double delta;
+    if (algo == MJB_ALGO_NPG && const_learn_rate > 0.0) {
+        alpha = (float)const_learn_rate;
+        delta = (double)(alpha * alpha * gx);
+    } else {
+        delta = algo == MJB_ALGO_NPG ? step_size_or_kl : 2.0 * step_size_or_kl;
+        alpha = sqrtf(fabsf((float)delta / (gx + 1e-20f)));
+    }
+    auto apply = [&](float al) -> int {
+        e->h_dsc[DS_ALPHA] = (double)al;
+        CK(e, cudaMemcpyAsync(e->dsc + DS_ALPHA, e->h_dsc + DS_ALPHA, sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        launch_axpy_clamp(e->pold.theta, e->x, e->dsc + DS_ALPHA, 1.0, e->d, e->A, e->cfg.min_log_std, e->pnew.theta, e->stream);
+        e->launches += 1;
+        if (set_params(e, e->pnew, nullptr)) return -1;
+        e->old_equals_new = false;
+        return 0;
+    };
+    double ev[2] = {0, 0};
+    if (algo == MJB_ALGO_TRPO) {
+        // trpo.py:108-120: shrink by 0.9 until KL < kl_dist (at most 100 probes, then alpha = 0)
+        bool accepted = false;
+        for (int k = 0; k < 100; ++k) {
+            if (apply(alpha) || eval_device(e, ev)) return -1;
+            if (ev[1] < step_size_or_kl) { accepted = true; break; }
+            alpha = 0.9f * alpha;
+            st.backtracks += 1;
+            if (k == 99) alpha = 0.0f;
+        }
+        if (!accepted) { if (apply(alpha) || eval_device(e, ev)) return -1; }
+    } else {
+        if (apply(alpha) || eval_device(e, ev)) return -1;
+    }
+    CK(e, cudaEventRecord(e->ev[3], e->stream));
+    st.alpha = alpha; st.delta = delta; st.surr_after = ev[0]; st.kl_dist = ev[1];
+    // old <- new (set_param_values(new, set_new=True, set_old=True), npg_cg.py:142)
+    CK(e, cudaMemcpyAsync(e->pold.theta, e->pnew.theta, sizeof(float) * e->d, cudaMemcpyDeviceToDevice, e->stream));
+    CK(e, cudaMemcpyAsync(e->pold.prep, e->pnew.prep, sizeof(float) * e->prep_total, cudaMemcpyDeviceToDevice, e->stream));
+    e->old_equals_new = e->transforms_equal;
+    e->old_cache_valid = false;
+    CK(e, cudaStreamSynchronize(e->stream));
+    cudaEventElapsedTime(&st.time_vpg_ms, e->ev[0], e->ev[1]);
+    cudaEventElapsedTime(&st.time_npg_ms, e->ev[1], e->ev[2]);
+    cudaEventElapsedTime(&st.time_eval_ms, e->ev[2], e->ev[3]);
+    cudaEventElapsedTime(&e->last_fvp_ms, e->ev[4], e->ev[5]);
+    if (out) *out = st;
+    return 0;
+}
+
+int mjb_policy_last_vectors(mjb_engine* e, float* vpg_out, float* npg_out) {
+    if (vpg_out && d2any(e, vpg_out, e->g, sizeof(float) * e->d)) return -1;
+    if (npg_out && d2any(e, npg_out, e->x, sizeof(float) * e->d)) return -1;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ baseline
+int mjb_vf_dim(const mjb_engine* e) { return e->vf_d; }
+
+int mjb_vf_set_state(mjb_engine* e, const float* w, const float* m, const float* v, int64_t step) {
+    if (w) CK(e, cudaMemcpyAsync(e->vf_w, w, sizeof(float) * e->vf_d, cudaMemcpyDefault, e->stream));
+    if (m) CK(e, cudaMemcpyAsync(e->vf_m, m, sizeof(float) * e->vf_d, cudaMemcpyDefault, e->stream));
+    if (v) CK(e, cudaMemcpyAsync(e->vf_v, v, sizeof(float) * e->vf_d, cudaMemcpyDefault, e->stream));
+    if (step >= 0) e->vf_step = step;
+    launch_prep_mlp(e->vf_w, e->VPL, e->vf_prep, e->stream);
+    e->launches += 1;
+    CK(e, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int mjb_vf_get_state(mjb_engine* e, float* w, float* m, float* v, int64_t* step) {
+    if (w && d2any(e, w, e->vf_w, sizeof(float) * e->vf_d)) return -1;
+    if (m && d2any(e, m, e->vf_m, sizeof(float) * e->vf_d)) return -1;
+    if (v && d2any(e, v, e->vf_v, sizeof(float) * e->vf_d)) return -1;
+    if (step) *step = e->vf_step;
+    return 0;
+}
+
+static int vf_error(mjb_engine* e, double* err) {
+    if (mjb_vf_predict(e)) return -1;
+    launch_vf_error(e->ret, e->base, e->n_roll, e->mom_scratch, e->dsc + DS_VF, e->stream);
+    e->launches += 2;
+    if (allreduce(e, e->dsc + DS_VF, 2, ncclDouble)) return -1;
+    CK(e, cudaMemcpyAsync(e->h_dsc + DS_VF, e->dsc + DS_VF, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    *err = e->h_dsc[DS_VF] / (e->h_dsc[DS_VF + 1] + 1e-8);
+    return 0;
+}
+
+int mjb_vf_fit(mjb_engine* e, const int32_t* perms, int epochs, int batch_size, float lr, float reg_coef, double err_out[2]) {
+    const long long N = e->n_glob_roll;
+    const int steps = (int)(N / batch_size) - 1;            // optimize_model.py:24
+    if (steps < 1) FAIL(e, "MLPBaseline.fit needs at least 2*batch_size samples (the reference crashes: optimize_model.py:24,35)");
+    if (err_out && vf_error(e, &err_out[0])) return -1;
+    const float* fobs = e->obs; const int* ftstep = e->tstep; const double* fret = e->ret;
+    if (e->comm) {
+        // replicated sequential fit: gather every rank's (obs, tstep, returns) in rank order
+        if (N > e->fit_cap) {
+            if (e->fit_obs) { cudaFree(e->fit_obs); cudaFree(e->fit_tstep); cudaFree(e->fit_ret); }
+            e->fit_cap = N;
+            CK(e, cudaMalloc(&e->fit_obs, sizeof(float) * N * e->cfg.obs_dim));
+            CK(e, cudaMalloc(&e->fit_tstep, sizeof(int) * N));
+            CK(e, cudaMalloc(&e->fit_ret, sizeof(double) * N));
+        }
+        std::vector<double> cnt(e->cfg.world_size, 0.0);
+        cnt[e->cfg.rank] = (double)e->n_roll;
+        double* dcnt = e->mom_scratch;                       // reuse (world_size <= 512)
+        CK(e, cudaMemcpyAsync(dcnt, cnt.data(), sizeof(double) * cnt.size(), cudaMemcpyHostToDevice, e->stream));
+        if (allreduce(e, dcnt, cnt.size(), ncclDouble)) return -1;
+        CK(e, cudaMemcpyAsync(cnt.data(), dcnt, sizeof(double) * cnt.size(), cudaMemcpyDeviceToHost, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));
+        NK(e, g_nccl.GroupStart());
+        long long off = 0;
+        for (int r = 0; r < e->cfg.world_size; ++r) {
+            const long long c = (long long)cnt[r];
+            NK(e, g_nccl.Broadcast(e->obs, e->fit_obs + off * e->cfg.obs_dim, c * e->cfg.obs_dim, ncclFloat, r, e->comm, e->stream));
+            NK(e, g_nccl.Broadcast(e->tstep, e->fit_tstep + off, c, ncclInt32, r, e->comm, e->stream));
+            NK(e, g_nccl.Broadcast(e->ret, e->fit_ret + off, c, ncclDouble, r, e->comm, e->stream));
+            off += c;
+        }
+        NK(e, g_nccl.GroupEnd());
+        fobs = e->fit_obs; ftstep = e->fit_tstep; fret = e->fit_ret;
+    }
+    if (N > e->perm_cap) {
+        if (e->perm_dev) cudaFree(e->perm_dev);
+        e->perm_cap = N;
+        CK(e, cudaMalloc(&e->perm_dev, sizeof(int) * N));
+    }
+    for (int ep = 0; ep < epochs; ++ep) {
+        CK(e, cudaMemcpyAsync(e->perm_dev, perms + (size_t)ep * N, sizeof(int) * N, cudaMemcpyDefault, e->stream));
+        if (e->comm) NK(e, g_nccl.Broadcast(e->perm_dev, e->perm_dev, N, ncclInt32, 0, e->comm, e->stream));
+        VfFitArgs a;
+        a.K = e->cfg.obs_dim + 4; a.H1 = e->cfg.vf_hidden[0]; a.H2 = e->cfg.vf_hidden[1]; a.obs_dim = e->cfg.obs_dim;
+        a.obs = fobs; a.tstep = ftstep; a.returns = fret; a.n = N; a.perm = e->perm_dev;
+        a.steps = steps; a.batch = batch_size; a.lr = lr; a.reg = reg_coef; a.beta1 = 0.9f; a.beta2 = 0.999f; a.eps = 1e-8f;
+        a.step0 = e->vf_step; a.w = e->vf_w; a.m = e->vf_m; a.v = e->vf_v; a.wT = e->vf_wT; a.loss_out = nullptr;
+        cudaError_t ce = launch_vf_fit(a, e->stream);
+        if (ce != cudaSuccess) FAIL(e, std::string("vf fit launch (batch<=64, multiple of 4; sizes must fit 220 KB smem): ") + cudaGetErrorString(ce));
+        e->launches += 1;
+        e->vf_step += steps;
+        CK(e, cudaStreamSynchronize(e->stream));             // the host permutation buffer may be reused by the caller
+    }
+    launch_prep_mlp(e->vf_w, e->VPL, e->vf_prep, e->stream);
+    e->launches += 1;
+    if (err_out && vf_error(e, &err_out[1])) return -1;
+    CK(e, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int64_t mjb_kernel_launches(const mjb_engine* e) { return e->launches; }
+int mjb_fvp_timing(mjb_engine* e, float* last_ms) { *last_ms = e->last_fvp_ms; return 0; }
+
+}  // extern "C"

@@ -1,0 +1,4 @@
+#include "mlp_inst.cuh"
+namespace mjb {
+MJB_DEFINE_MLP(128, 128)
+}

@@ -1,0 +1,250 @@
+"""Python handle over the C-ABI engine (include/mjrl_b200.h).  Host arrays are numpy; device memory,
+streams and kernels live behind the library.  torch is used only for torch.distributed plumbing
+(broadcasting the NCCL unique id when world_size > 1)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _native
+from ._native import BatchStats, Config, MjbError, StepStats
+
+ALGO = {"npg": 0, "trpo": 1, "dapg": 2}
+ROLLOUT, DEMO = 0, 1
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Engine:
+    """One engine per GPU / per rank.  Not thread-safe (neither is mjrl)."""
+
+    def __init__(self, obs_dim, act_dim, hidden=(64, 64), vf_hidden=(128, 128), min_log_std=-3.0,
+                 max_samples=1 << 16, max_paths=4096, device=0, world_size=1, rank=0):
+        self.lib = _native.load()
+        hidden = tuple(int(h) for h in hidden)
+        if len(hidden) not in (0, 2):
+            raise NotImplementedError("mjrl_b200 supports LinearPolicy (no hidden layer) and 2-hidden-layer MLPs "
+                                      "(the reference MLP is '2 layers only', gaussian_mlp.py:15)")
+        cfg = Config()
+        cfg.device, cfg.obs_dim, cfg.act_dim, cfg.n_hidden = int(device), int(obs_dim), int(act_dim), len(hidden)
+        for i, h in enumerate(hidden):
+            cfg.hidden[i] = h
+        cfg.vf_hidden[0], cfg.vf_hidden[1] = int(vf_hidden[0]), int(vf_hidden[1])
+        cfg.min_log_std = float(min_log_std)
+        cfg.max_samples, cfg.max_paths = int(max_samples), int(max_paths)
+        cfg.world_size, cfg.rank = int(world_size), int(rank)
+        self.cfg = cfg
+        self.obs_dim, self.act_dim, self.hidden, self.vf_hidden = int(obs_dim), int(act_dim), hidden, tuple(vf_hidden)
+        self.max_samples, self.max_paths = int(max_samples), int(max_paths)
+        self.world_size, self.rank = int(world_size), int(rank)
+        h = C.c_void_p()
+        if self.lib.mjb_create(C.byref(cfg), C.byref(h)) != 0:
+            raise MjbError("mjb_create: " + self.lib.mjb_last_error(None).decode())
+        self.h = h
+        self.d = self.lib.mjb_policy_dim(h)
+        self.vf_d = self.lib.mjb_vf_dim(h)
+        self.n = 0
+        self.n_demo = 0
+        self._keep = None
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mjb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise MjbError("%s: %s" % (what, self.lib.mjb_last_error(self.h).decode()))
+
+    def synchronize(self):
+        self._ck(self.lib.mjb_synchronize(self.h), "synchronize")
+
+    def init_comm(self):
+        """Create the engine-owned NCCL communicator; the unique id travels over torch.distributed."""
+        if self.world_size == 1:
+            return
+        import torch
+        import torch.distributed as dist
+        buf = (C.c_char * 128)()
+        if self.rank == 0 and self.lib.mjb_comm_unique_id(buf) != 0:
+            raise MjbError("mjb_comm_unique_id: " + self.lib.mjb_last_error(None).decode())
+        t = torch.frombuffer(bytearray(bytes(buf)), dtype=torch.uint8).clone()
+        if dist.get_backend() == "nccl":
+            t = t.cuda(self.cfg.device)
+        dist.broadcast(t, src=0)
+        raw = bytes(t.cpu().numpy().tobytes())
+        self._ck(self.lib.mjb_comm_init(self.h, C.c_char_p(raw)), "comm_init")
+
+    # ------------------------------------------------------------------ trajectories
+    def upload_paths(self, paths, which=ROLLOUT):
+        """paths: list of mjrl path dicts (samplers/core.py:85-92).  float64 arrays are passed by pointer."""
+        n_paths = len(paths)
+        keep, ptrs = [], []
+        for key in ("observations", "actions", "rewards"):
+            if key == "rewards" and which == DEMO:
+                ptrs.append(None)
+                continue
+            arrs = [np.ascontiguousarray(p[key], dtype=np.float64) for p in paths]
+            keep.append(arrs)
+            ptrs.append((C.c_void_p * n_paths)(*[a.ctypes.data for a in arrs]))
+        lens = np.array([len(p["actions"]) for p in paths], dtype=np.int32)
+        term = np.array([bool(p.get("terminated", False)) for p in paths], dtype=np.uint8)
+        self._ck(self.lib.mjb_batch_upload(self.h, which, n_paths, ptrs[0], ptrs[1], ptrs[2], _ptr(lens), _ptr(term)),
+                 "batch_upload")
+        if which == ROLLOUT:
+            self.n, self.n_demo, self.lens = int(lens.sum()), 0, lens
+        else:
+            self.n_demo = int(lens.sum())
+        return self.n
+
+    def upload_flat(self, obs, act, rew, lens, terminated, which=ROLLOUT):
+        obs = np.ascontiguousarray(obs, dtype=np.float64)
+        act = np.ascontiguousarray(act, dtype=np.float64)
+        rew = None if rew is None else np.ascontiguousarray(rew, dtype=np.float64)
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        term = np.ascontiguousarray(terminated, dtype=np.uint8)
+        self._ck(self.lib.mjb_batch_upload_flat(self.h, which, len(lens), _ptr(obs), _ptr(act), _ptr(rew), _ptr(lens),
+                                                _ptr(term)), "batch_upload_flat")
+        if which == ROLLOUT:
+            self.n, self.n_demo, self.lens = int(lens.sum()), 0, lens
+        else:
+            self.n_demo = int(lens.sum())
+        return self.n
+
+    def set_advantages(self, adv_concat):
+        a = np.ascontiguousarray(adv_concat, dtype=np.float64)
+        assert a.shape[0] == self.n
+        self._ck(self.lib.mjb_batch_set_advantages(self.h, _ptr(a)), "set_advantages")
+
+    # ------------------------------------------------------------------ returns / advantages
+    def compute_returns(self, gamma):
+        self._ck(self.lib.mjb_compute_returns(self.h, float(gamma)), "compute_returns")
+
+    def vf_predict(self):
+        self._ck(self.lib.mjb_vf_predict(self.h), "vf_predict")
+
+    def compute_advantages(self, gamma, gae_lambda):
+        use_gae = gae_lambda is not None and 0.0 <= gae_lambda <= 1.0
+        self._ck(self.lib.mjb_compute_advantages(self.h, float(gamma), float(gae_lambda) if use_gae else 0.0,
+                                                 int(use_gae)), "compute_advantages")
+
+    def _get(self, fn, dtype):
+        out = np.empty(self.n, dtype=dtype)
+        self._ck(fn(self.h, _ptr(out)), fn.__name__)
+        return out
+
+    def returns(self):
+        return self._get(self.lib.mjb_get_returns, np.float64)
+
+    def baseline(self):
+        return self._get(self.lib.mjb_get_baseline, np.float32)
+
+    def advantages(self):
+        return self._get(self.lib.mjb_get_advantages, np.float64)
+
+    def adv_white(self):
+        return self._get(self.lib.mjb_get_adv_white, np.float32)
+
+    def process_paths(self):
+        st = BatchStats()
+        self._ck(self.lib.mjb_process_paths(self.h, C.byref(st)), "process_paths")
+        return st
+
+    # ------------------------------------------------------------------ policy
+    def set_params(self, theta, set_new=True, set_old=True):
+        th = _f32(theta)
+        assert th.shape[0] == self.d, "parameter vector has %d entries, engine expects %d" % (th.shape[0], self.d)
+        self._ck(self.lib.mjb_policy_set_params(self.h, _ptr(th), int(set_new), int(set_old)), "set_params")
+        self.synchronize()
+
+    def get_params(self, old=False):
+        out = np.empty(self.d, dtype=np.float32)
+        self._ck(self.lib.mjb_policy_get_params(self.h, _ptr(out), int(old)), "get_params")
+        return out
+
+    def set_transforms(self, in_shift=None, in_scale=None, out_shift=None, out_scale=None, old=False):
+        arrs = [None if a is None else _f32(a) for a in (in_shift, in_scale, out_shift, out_scale)]
+        self._ck(self.lib.mjb_policy_set_transforms(self.h, *[_ptr(a) for a in arrs], int(old)), "set_transforms")
+
+    def eval(self):
+        out = (C.c_double * 2)()
+        self._ck(self.lib.mjb_policy_eval(self.h, C.byref(out)), "policy_eval")
+        return out[0], out[1]
+
+    def vpg(self, include_demo=False, demo_lam=0.0):
+        g = np.empty(self.d, dtype=np.float32)
+        self._ck(self.lib.mjb_policy_vpg(self.h, int(include_demo), float(demo_lam), _ptr(g)), "policy_vpg")
+        return g
+
+    def fvp(self, v, damping, idx=None):
+        v = _f32(v)
+        out = np.empty(self.d, dtype=np.float32)
+        ii = None if idx is None else np.ascontiguousarray(idx, dtype=np.int32)
+        self._ck(self.lib.mjb_policy_fvp(self.h, _ptr(v), float(damping), _ptr(ii), 0 if ii is None else ii.shape[0],
+                                         _ptr(out)), "policy_fvp")
+        return out
+
+    def cg(self, b=None, iters=10, damping=1e-4, tol=1e-10, idx=None):
+        bb = None if b is None else _f32(b)
+        x = np.empty(self.d, dtype=np.float32)
+        ii = None if idx is None else np.ascontiguousarray(idx, dtype=np.int32).reshape(iters, -1)
+        self._ck(self.lib.mjb_policy_cg(self.h, _ptr(bb), int(iters), float(damping), float(tol), _ptr(ii),
+                                        0 if ii is None else ii.shape[1], _ptr(x)), "policy_cg")
+        return x
+
+    def step(self, algo="npg", step_size=0.01, const_learn_rate=None, cg_iters=10, damping=1e-4, demo_lam=0.0,
+             hvp_idx=None):
+        st = StepStats()
+        ii = None if hvp_idx is None else np.ascontiguousarray(hvp_idx, dtype=np.int32).reshape(cg_iters, -1)
+        self._ck(self.lib.mjb_policy_step(self.h, ALGO[algo], float(step_size),
+                                          -1.0 if const_learn_rate is None else float(const_learn_rate),
+                                          int(cg_iters), float(damping), float(demo_lam), _ptr(ii),
+                                          0 if ii is None else ii.shape[1], C.byref(st)), "policy_step")
+        return st
+
+    def last_vectors(self):
+        g = np.empty(self.d, dtype=np.float32)
+        x = np.empty(self.d, dtype=np.float32)
+        self._ck(self.lib.mjb_policy_last_vectors(self.h, _ptr(g), _ptr(x)), "last_vectors")
+        return g, x
+
+    # ------------------------------------------------------------------ baseline
+    def vf_set_state(self, w, m=None, v=None, step=-1):
+        arrs = [None if a is None else _f32(a) for a in (w, m, v)]
+        self._ck(self.lib.mjb_vf_set_state(self.h, *[_ptr(a) for a in arrs], int(step)), "vf_set_state")
+
+    def vf_get_state(self):
+        w, m, v = (np.empty(self.vf_d, dtype=np.float32) for _ in range(3))
+        step = C.c_int64()
+        self._ck(self.lib.mjb_vf_get_state(self.h, _ptr(w), _ptr(m), _ptr(v), C.byref(step)), "vf_get_state")
+        return w, m, v, int(step.value)
+
+    def vf_fit(self, perms, batch_size=64, lr=1e-3, reg_coef=0.0, return_errors=False):
+        perms = np.ascontiguousarray(perms, dtype=np.int32)
+        if perms.ndim == 1:
+            perms = perms[None]
+        err = (C.c_double * 2)()
+        self._ck(self.lib.mjb_vf_fit(self.h, _ptr(perms), perms.shape[0], int(batch_size), float(lr), float(reg_coef),
+                                     C.byref(err) if return_errors else None), "vf_fit")
+        return (err[0], err[1]) if return_errors else None
+
+    # ------------------------------------------------------------------ introspection
+    def kernel_launches(self):
+        return int(self.lib.mjb_kernel_launches(self.h))
+
+    def last_fvp_ms(self):
+        t = C.c_float()
+        self.lib.mjb_fvp_timing(self.h, C.byref(t))
+        return float(t.value)

@@ -1,0 +1,242 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) against the golden fixtures produced by the real
+reference and against the CPU oracle on the same seeded inputs.
+
+Tolerances (fp32 path; reference self-noise between 1 and 8 CPU threads is 2.5e-7 on the FVP and 3e-6 on
+the CG direction):
+  returns ........ bit-exact;  GAE: bit-exact given identical baseline predictions
+  VPG / FVP ...... rel-L2 <= 1e-5
+  CG direction ... 1 - cos <= 1e-4 (north_star), tighter where N >> d
+  surrogate / KL / alpha ... rel <= 1e-3
+"""
+import numpy as np
+import pytest
+
+from conftest import ALL_CASES, golden_paths, load_golden, one_minus_cos, rel
+from oracle import npg_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def make_engine(g, cuda_device, demo=0):
+    from mjrl_b200.engine import Engine
+    m = g["meta"]
+    n = int(g["path_len"].sum())
+    eng = Engine(m["obs_dim"], m["act_dim"], m["hidden"], max_samples=n + demo + 8, max_paths=len(g["path_len"]) + 1)
+    eng.set_params(g["theta0"])
+    eng.vf_set_state(g["vf_w0"], np.zeros_like(g["vf_w0"]), np.zeros_like(g["vf_w0"]), 0)
+    return eng
+
+
+def well_conditioned(g):
+    n = int(g["path_len"].sum())
+    d = g["theta0"].shape[0]
+    return n * g["meta"]["act_dim"] > 4 * d or len(g["meta"]["hidden"]) == 0
+
+
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_returns_gae(case, cuda_device):
+    g = load_golden(case)
+    paths = golden_paths(g)
+    m = g["meta"]
+    eng = make_engine(g, cuda_device)
+    eng.upload_paths(paths)
+    eng.compute_returns(m["gamma"])
+    assert np.array_equal(eng.returns(), g["returns"])            # bit-exact fp64 scan
+    eng.vf_predict()
+    base = eng.baseline()
+    np.testing.assert_allclose(base, g["baseline"], rtol=0, atol=5e-6)
+    eng.compute_advantages(m["gamma"], m["lam"])
+    adv = eng.advantages()
+    # bit-exact against the reference formula evaluated on the engine's own baseline predictions
+    k = 0
+    for p in paths:
+        T = len(p["rewards"])
+        want = O.gae_path(p["rewards"], base[k:k + T], p["terminated"], m["gamma"], m["lam"])
+        assert np.array_equal(adv[k:k + T], want)
+        k += T
+    np.testing.assert_allclose(adv, g["advantages"], rtol=0, atol=2e-4)
+    eng.compute_advantages(m["gamma"], None)
+    assert np.array_equal(eng.advantages(), g["returns"] - base.astype(np.float64))
+    # whitening + return statistics, from the reference's own advantages
+    eng.set_advantages(g["advantages"])
+    st = eng.process_paths()
+    np.testing.assert_allclose(eng.adv_white(), g["adv_white"].astype(np.float32), rtol=0, atol=1e-6)
+    np.testing.assert_allclose([st.mean_return, st.std_return, st.min_return, st.max_return], g["base_stats"],
+                               rtol=1e-12)
+    eng.close()
+
+
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_vpg_fvp_eval(case, cuda_device):
+    g = load_golden(case)
+    paths = golden_paths(g)
+    eng = make_engine(g, cuda_device)
+    eng.upload_paths(paths)
+    eng.set_advantages(g["advantages"])
+    eng.process_paths()
+    vpg = eng.vpg()
+    assert rel(vpg, g["vpg"]) < 1e-5
+    fv = eng.fvp(g["fvp_vec"], g["meta"]["damping"])
+    assert rel(fv, g["fvp_out"]) < 1e-5
+    surr, kl = eng.eval()
+    assert abs(surr - g["surr0"]) < 1e-6 and kl == 0.0
+    # new != old: surrogate / KL / gradient at the perturbed parameters
+    eng.set_params(g["theta_pert"], set_new=True, set_old=False)
+    surr, kl = eng.eval()
+    assert abs(surr - g["surr_pert"]) < 1e-3 * max(1.0, abs(g["surr_pert"]))
+    assert abs(kl - g["kl_pert"]) < 1e-3 * max(1e-3, g["kl_pert"])
+    assert rel(eng.vpg(), g["vpg_pert"]) < 2e-5
+    # CG direction from the reference's own gradient
+    eng.set_params(g["theta0"])
+    x = eng.cg(g["vpg"], iters=g["meta"]["cg_iters"], damping=g["meta"]["damping"])
+    assert one_minus_cos(x, g["cg_x"]) < (1e-6 if well_conditioned(g) else 5e-3)
+    eng.close()
+
+
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_policy_steps(case, cuda_device):
+    g = load_golden(case)
+    paths = golden_paths(g)
+    m = g["meta"]
+    th = g["theta0"]
+    wc = well_conditioned(g)
+    ctol, stol = (1e-4, 2e-3) if wc else (5e-3, 3e-2)
+    demo = golden_paths(g, demo=True)
+    eng = make_engine(g, cuda_device, demo=sum(len(p["rewards"]) for p in demo))
+
+    def fresh():
+        eng.upload_paths(paths)
+        eng.set_params(th)
+        eng.set_advantages(g["advantages"])
+        eng.process_paths()
+
+    fresh()
+    st = eng.step("npg", step_size=m["npg_step"], cg_iters=m["cg_iters"], damping=m["damping"])
+    new = eng.get_params()
+    assert one_minus_cos(new - th, g["npg_theta"] - th) < ctol
+    if wc:
+        assert rel(new, g["npg_theta"]) < 1e-4
+    assert abs(st.alpha / g["npg_alpha"] - 1) < stol
+    assert abs(st.kl_dist / g["npg_kl_dist"] - 1) < 3 * stol
+    assert abs((st.surr_after - st.surr_before) / g["npg_surr_improvement"] - 1) < 3 * stol
+    assert np.array_equal(eng.get_params(old=True), new)
+    for tag, kl in (("trpo", 0.01), ("trpo_big", 0.5)):
+        fresh()
+        st = eng.step("trpo", step_size=kl, cg_iters=m["cg_iters"], damping=m["damping"])
+        assert st.backtracks == int(g[tag + "_backtracks"])
+        assert one_minus_cos(eng.get_params() - th, g[tag + "_theta"] - th) < ctol
+        assert abs(st.alpha / g[tag + "_alpha"] - 1) < stol
+        assert abs(st.kl_dist / g[tag + "_kl_dist"] - 1) < 3 * stol
+    fresh()
+    eng.upload_paths(demo, which=1)
+    st = eng.step("dapg", step_size=0.01, cg_iters=m["cg_iters"], damping=m["damping"], demo_lam=1.0 * 0.95 ** 3.0)
+    assert one_minus_cos(eng.get_params() - th, g["dapg_theta"] - th) < ctol
+    assert abs(st.alpha / g["dapg_alpha"] - 1) < stol
+    fresh()
+    st = eng.step("npg", step_size=m["npg_step"], cg_iters=m["cg_iters"], damping=m["damping"], hvp_idx=g["sub_idx"])
+    assert one_minus_cos(eng.get_params() - th, g["sub_theta"] - th) < ctol
+    eng.close()
+
+
+@pytest.mark.parametrize("case", ["pm_5x50", "pm_40x25_ragged", "swim_40x250", "linear_30x200"])
+def test_baseline_fit(case, cuda_device):
+    g = load_golden(case)
+    paths = golden_paths(g)
+    eng = make_engine(g, cuda_device)
+    eng.upload_paths(paths)
+    eng.compute_returns(g["meta"]["gamma"])
+    err = eng.vf_fit(g["fit_perms"][:2], 64, 1e-3, 1e-3, return_errors=True)
+    np.testing.assert_allclose(err, g["fit1_err"], rtol=2e-4)
+    w, mm, vv, step = eng.vf_get_state()
+    assert rel(w, g["fit1_w"]) < 1e-4
+    eng.vf_fit(g["fit_perms"][2:4], 64, 1e-3, 1e-3)
+    w, mm, vv, step = eng.vf_get_state()
+    assert step == int(g["fit2_step"])
+    assert rel(w, g["fit2_w"]) < 2e-2                     # see tests/test_oracle.py: dead-unit drift under Adam
+    assert rel(vv, g["fit2_v"]) < 1e-3
+    eng.vf_predict()
+    np.testing.assert_allclose(eng.baseline(), g["fit2_predict"], rtol=0, atol=2e-4)
+    eng.close()
+
+
+def test_fit_too_small_raises(cuda_device):
+    from mjrl_b200.engine import Engine, MjbError
+    paths = O.synthetic_paths(3, 1, 2, 50, seed=0)
+    eng = Engine(3, 1, (32, 32), max_samples=256, max_paths=8)
+    eng.upload_paths(paths)
+    eng.compute_returns(0.9)
+    with pytest.raises(MjbError):
+        eng.vf_fit(np.arange(100, dtype=np.int32))
+    eng.close()
+
+
+def test_empty_and_ragged_edges(cuda_device):
+    """Length-1 paths, a single path, unequal lengths crossing tile boundaries."""
+    from mjrl_b200.engine import Engine
+    rng = np.random.RandomState(3)
+    lens = [1, 257, 1, 130, 2, 511]
+    paths = [dict(observations=rng.randn(T, 5), actions=rng.randn(T, 3), rewards=rng.randn(T),
+                  terminated=bool(i % 2)) for i, T in enumerate(lens)]
+    spec = O.PolicySpec(5, 3, (64, 64))
+    th = O.init_policy_params(spec, 1)
+    eng = Engine(5, 3, (64, 64), max_samples=1024, max_paths=8)
+    eng.set_params(th)
+    vf = O.VFState(5, (128, 128), seed=2)
+    eng.vf_set_state(vf.w)
+    eng.upload_paths(paths)
+    eng.compute_returns(0.99)
+    assert np.array_equal(eng.returns(), np.concatenate([O.discount_sum(p["rewards"], 0.99) for p in paths]))
+    eng.vf_predict()
+    base = eng.baseline()
+    np.testing.assert_allclose(base, np.concatenate([O.vf_predict(vf, p) for p in paths]), atol=5e-6, rtol=0)
+    eng.compute_advantages(0.99, 0.95)
+    adv = eng.advantages()
+    k = 0
+    for p in paths:
+        T = len(p["rewards"])
+        assert np.array_equal(adv[k:k + T], O.gae_path(p["rewards"], base[k:k + T], p["terminated"], 0.99, 0.95))
+        k += T
+    eng.process_paths()
+    obs = np.concatenate([p["observations"] for p in paths])
+    act = np.concatenate([p["actions"] for p in paths])
+    white = eng.adv_white()
+    assert rel(eng.vpg(), O.flat_vpg(spec, th, obs, act, white)) < 1e-5
+    v = rng.randn(spec.d).astype(np.float32)
+    assert rel(eng.fvp(v, 1e-4), O.fvp(spec, th, obs, v, 1e-4)) < 1e-5
+    eng.close()
+
+
+@pytest.mark.parametrize("shape", [(39, 28, (256, 256), 3000), (70, 4, (64, 32), 2000), (376, 17, (), 3000),
+                                   (3, 1, (32, 32), 1500), (45, 9, (100, 60), 1800)])
+def test_shapes_vs_oracle(shape, cuda_device):
+    """Shapes outside the goldens (cfg4 door 39/28 256x256, cfg5 humanoid-linear 376/17, unequal / unpadded
+    hidden widths, obs wider than one 32-feature chunk) against the fp64 closed-form oracle."""
+    from mjrl_b200.engine import Engine
+    obs_dim, act_dim, hidden, n = shape
+    rng = np.random.RandomState(7)
+    paths = O.synthetic_paths(obs_dim, act_dim, 6, n // 6, seed=11, ragged=True)
+    spec = O.PolicySpec(obs_dim, act_dim, hidden)
+    th = O.init_policy_params(spec, 3)
+    th[-act_dim:] = 0.1 * rng.randn(act_dim)                      # non-trivial log_std
+    eng = Engine(obs_dim, act_dim, hidden, max_samples=n + 8, max_paths=8)
+    eng.set_params(th)
+    eng.upload_paths(paths)
+    N = eng.n
+    adv = rng.randn(N)
+    eng.set_advantages(adv)
+    eng.process_paths()
+    obs = np.concatenate([p["observations"] for p in paths])
+    act = np.concatenate([p["actions"] for p in paths])
+    white = O.whiten(adv)
+    assert rel(eng.vpg(), O.flat_vpg(spec, th, obs, act, white)) < 1e-5
+    v = rng.randn(spec.d).astype(np.float32)
+    assert rel(eng.fvp(v, 1e-4), O.fvp(spec, th, obs, v, 1e-4)) < 1e-5
+    idx = rng.randint(0, N, size=N // 2).astype(np.int32)
+    assert rel(eng.fvp(v, 1e-4, idx=idx), O.fvp(spec, th, obs[idx], v, 1e-4)) < 1e-5
+    th2 = spec.clamp(th + 0.01 * rng.randn(spec.d).astype(np.float32))
+    eng.set_params(th2, set_new=True, set_old=False)
+    surr, kl = eng.eval()
+    assert abs(surr - float(O.surrogate(spec, th2, th, obs, act, white))) < 1e-4
+    assert abs(kl / float(O.mean_kl(spec, th2, th, obs)) - 1) < 1e-3
+    assert rel(eng.vpg(), O.flat_vpg(spec, th2, obs, act, white, theta_old=th)) < 2e-5
+    eng.close()
