@@ -42,13 +42,15 @@ typedef struct mjb_config {
     int32_t rank;
 } mjb_config;
 
-/* Scalars the reference logs after train_from_paths (algos/npg_cg.py:145-151, trpo.py:129-135). */
+/* Scalars the reference logs after train_from_paths (algos/npg_cg.py:145-151, algos/trpo.py:129-135). */
 typedef struct mjb_step_stats {
     double alpha, delta, kl_dist, surr_before, surr_after;
     double vpg_dot_npg;      /* g . x                                                                   */
-    int32_t backtracks;      /* TRPO line-search shrinks (trpo.py:108-120)                              */
+    int32_t backtracks;      /* TRPO line-search shrinks (algos/trpo.py:108-120)                             */
     int32_t cg_iters_run;    /* FVPs actually evaluated (early exit of utils/cg_solve.py:19-20)         */
     float time_vpg_ms, time_npg_ms, time_eval_ms;   /* CUDA-event timings of the phases                */
+    float fvp_kernel_ms_sum;  /* sum of CUDA-event durations of the FVP tile kernel launches of this step     */
+    int32_t fvp_launches;
 } mjb_step_stats;
 
 /* Return statistics of the rollout batch (algos/batch_reinforce.py:188-195). */
@@ -86,6 +88,15 @@ int  mjb_batch_upload_flat(mjb_engine* e, int which, int32_t n_paths, const doub
                            const double* rew, const int32_t* len, const uint8_t* terminated);
 /* Advantages computed elsewhere (callers of train_from_paths that bring path["advantages"]). */
 int  mjb_batch_set_advantages(mjb_engine* e, const double* adv_concat);
+/* Already-whitened advantages as the reference's CPI_surrogate / flat_vpg take them (fp32 after .float(),
+ * algos/batch_reinforce.py:41); replaces the output of mjb_process_paths. */
+int  mjb_batch_set_adv_white(mjb_engine* e, const float* adv_white);
+/* Baseline predictions computed elsewhere (non-MLP baselines keep working on the host: their
+ * predict(path) output, concatenated, fp32) -- consumed by mjb_compute_advantages. */
+int  mjb_batch_set_baseline(mjb_engine* e, const float* base_concat);
+/* Returns computed elsewhere (path["returns"], concatenated fp64) -- consumed by mjb_vf_fit. */
+int  mjb_batch_set_returns(mjb_engine* e, const double* ret_concat);
+/* which: MJB_BATCH_ROLLOUT / MJB_BATCH_DEMO = samples on this rank; 2 = rollout samples over all ranks */
 int64_t mjb_batch_size(const mjb_engine* e, int which);
 
 /* ---- returns / advantages (utils/process_samples.py:3-35) ----------------------------------- */
@@ -122,7 +133,7 @@ int  mjb_policy_fvp(mjb_engine* e, const float* v, float damping, const int32_t*
 int  mjb_policy_cg(mjb_engine* e, const float* b, int iters, float damping, float residual_tol,
                    const int32_t* idx, int64_t n_idx, float* x_out);
 /* One whole train_from_paths after process_paths: surrogate, VPG, CG, step size, update (+TRPO line
- * search), re-evaluation, old <- new (algos/npg_cg.py:109-142, trpo.py:83-126, dapg.py:92-121). */
+ * search), re-evaluation, old <- new (algos/npg_cg.py:109-142, algos/trpo.py:83-126, algos/dapg.py:92-121). */
 int  mjb_policy_step(mjb_engine* e, int algo, double step_size_or_kl, double const_learn_rate,
                      int cg_iters, float damping, double demo_lam, const int32_t* hvp_idx, int64_t n_idx,
                      mjb_step_stats* out);
@@ -140,6 +151,9 @@ int  mjb_vf_fit(mjb_engine* e, const int32_t* perms, int epochs, int batch_size,
                 double err_out[2]);
 
 /* ---- introspection for benchmarks ------------------------------------------------------------ */
+/* CUDA events on the engine's stream (slots 0..7) so callers time on the device, not by wall clock. */
+int  mjb_event_record(mjb_engine* e, int slot);
+int  mjb_event_elapsed_ms(mjb_engine* e, int slot_a, int slot_b, float* ms);   /* synchronises on slot_b */
 int64_t mjb_kernel_launches(const mjb_engine* e);        /* kernels launched by this engine so far    */
 int  mjb_fvp_timing(mjb_engine* e, float* last_ms);       /* CUDA-event time of the last FVP kernel    */
 

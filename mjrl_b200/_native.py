@@ -25,7 +25,8 @@ class StepStats(C.Structure):
     _fields_ = [("alpha", C.c_double), ("delta", C.c_double), ("kl_dist", C.c_double),
                 ("surr_before", C.c_double), ("surr_after", C.c_double), ("vpg_dot_npg", C.c_double),
                 ("backtracks", C.c_int32), ("cg_iters_run", C.c_int32), ("time_vpg_ms", C.c_float),
-                ("time_npg_ms", C.c_float), ("time_eval_ms", C.c_float)]
+                ("time_npg_ms", C.c_float), ("time_eval_ms", C.c_float), ("fvp_kernel_ms_sum", C.c_float),
+                ("fvp_launches", C.c_int32)]
 
 
 class BatchStats(C.Structure):
@@ -47,6 +48,9 @@ _SIGNATURES = {
     "mjb_batch_upload": (C.c_int, [_P, C.c_int, C.c_int32, _P, _P, _P, _P, _P]),
     "mjb_batch_upload_flat": (C.c_int, [_P, C.c_int, C.c_int32, _P, _P, _P, _P, _P]),
     "mjb_batch_set_advantages": (C.c_int, [_P, _P]),
+    "mjb_batch_set_baseline": (C.c_int, [_P, _P]),
+    "mjb_batch_set_returns": (C.c_int, [_P, _P]),
+    "mjb_batch_set_adv_white": (C.c_int, [_P, _P]),
     "mjb_batch_size": (C.c_int64, [_P, C.c_int]),
     "mjb_compute_returns": (C.c_int, [_P, C.c_double]),
     "mjb_vf_predict": (C.c_int, [_P]),
@@ -71,6 +75,8 @@ _SIGNATURES = {
     "mjb_vf_set_state": (C.c_int, [_P, _P, _P, _P, C.c_int64]),
     "mjb_vf_get_state": (C.c_int, [_P, _P, _P, _P, C.POINTER(C.c_int64)]),
     "mjb_vf_fit": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_double * 2)]),
+    "mjb_event_record": (C.c_int, [_P, C.c_int]),
+    "mjb_event_elapsed_ms": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "mjb_kernel_launches": (C.c_int64, [_P]),
     "mjb_fvp_timing": (C.c_int, [_P, C.POINTER(C.c_float)]),
 }

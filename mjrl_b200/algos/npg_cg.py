@@ -1,0 +1,83 @@
+"""Natural policy gradient agent with the reference's constructor and methods (mjrl/algos/npg_cg.py:24-163).
+`train_from_paths` is one call into the engine: VPG kernel -> device-resident CG (10 fused FVP + update
+pairs) -> step size -> parameter update -> fused surrogate/KL re-evaluation."""
+import time as timer
+
+import numpy as np
+
+from mjrl_b200.algos.batch_reinforce import BatchREINFORCE
+
+
+class NPG(BatchREINFORCE):
+    algo = "npg"
+
+    def __init__(self, env, policy, baseline, normalized_step_size=0.01, const_learn_rate=None,
+                 FIM_invert_args={'iters': 10, 'damping': 1e-4}, hvp_sample_frac=1.0, seed=123,
+                 save_logs=False, kl_dist=None, input_normalization=None, **kwargs):
+        self._setup(env, policy, baseline, seed, save_logs)
+        self.alpha = const_learn_rate
+        self.n_step_size = normalized_step_size if kl_dist is None else 2.0 * kl_dist
+        self.kl_dist = kl_dist if kl_dist is not None else 0.5 * normalized_step_size
+        self.FIM_invert_args = FIM_invert_args
+        self.hvp_subsample = hvp_sample_frac
+        self.input_normalization = input_normalization
+        if self.input_normalization is not None and not (0 < self.input_normalization <= 1):
+            self.input_normalization = None
+
+    # ---- reference-signature Fisher-vector product (npg_cg.py:62-88) ----
+    def HVP(self, observations, actions, vector, regu_coef=None):
+        regu_coef = self.FIM_invert_args['damping'] if regu_coef is None else regu_coef
+        eng = self._flat_batch(observations, actions)
+        idx = self._draw_hvp_indices(observations.shape[0], 1)
+        return eng.fvp(vector, regu_coef, None if idx is None else idx[0])
+
+    def build_Hvp_eval(self, inputs, regu_coef=None):
+        def eval(v):
+            return self.HVP(*(inputs + [v] + [regu_coef]))
+        return eval
+
+    def _draw_hvp_indices(self, n_local, iters):
+        """hvp_sample_frac < 0.99: np.random.choice(N, int(frac*N)) re-drawn for every product, from the global
+        numpy RNG at the reference's program point (npg_cg.py:65-69)."""
+        if self.hvp_subsample is None or self.hvp_subsample >= 0.99:
+            return None
+        if self._engine is not None and self._engine.world_size > 1:
+            raise NotImplementedError("hvp_sample_frac < 1 with world_size > 1")
+        return np.stack([np.random.choice(n_local, size=int(self.hvp_subsample * n_local))
+                         for _ in range(iters)]).astype(np.int32)
+
+    def _normalize_inputs(self, eng, paths):
+        """npg_cg.py:101-107: running average of the observation moments into policy.model ONLY (old_model keeps
+        the stale transform -- reproduced literally)."""
+        if eng.world_size > 1:
+            raise NotImplementedError("input_normalization with world_size > 1")
+        obs = np.concatenate([p["observations"] for p in paths])
+        m = self.policy.model
+        a = self.input_normalization
+        in_shift = a * m.in_shift.numpy() + (1 - a) * np.mean(obs, axis=0)
+        in_scale = a * m.in_scale.numpy() + (1 - a) * np.std(obs, axis=0)
+        m.set_transformations(in_shift, in_scale, m.out_shift.numpy(), m.out_scale.numpy())
+        self._pushed = None
+        self._push_policy(eng)
+
+    def _step_args(self):
+        return dict(step_size=self.n_step_size, const_learn_rate=self.alpha)
+
+    def _demo_lam(self, eng):
+        return 0.0
+
+    def train_from_paths(self, paths):
+        t0 = timer.time()
+        _, _, _, base_stats, self.running_score = self.process_paths(paths)
+        eng = self._engine
+        if self.save_logs:
+            self.log_rollout_statistics(paths, base_stats)
+        if getattr(self, "input_normalization", None):
+            self._normalize_inputs(eng, paths)
+        iters = self.FIM_invert_args['iters']
+        demo_lam = self._demo_lam(eng)
+        idx = self._draw_hvp_indices(eng.n, iters)
+        st = eng.step(self.algo, cg_iters=iters, damping=self.FIM_invert_args['damping'], demo_lam=demo_lam,
+                      hvp_idx=idx, **self._step_args())
+        self._finish_step(eng, st, paths, timer.time() - t0)
+        return base_stats

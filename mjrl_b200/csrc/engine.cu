@@ -107,6 +107,10 @@ struct mjb_engine {
     ncclComm_t comm = nullptr;
     // ---- timing
     cudaEvent_t ev[6];
+    cudaEvent_t user_ev[8];
+    static constexpr int kFvpRing = 128;
+    cudaEvent_t fvp_ev[kFvpRing][2];
+    long long fvp_count = 0;
     float last_fvp_ms = 0.f;
 };
 
@@ -238,10 +242,13 @@ int fvp_device(mjb_engine* e, const float* v, const int* idx, long long n_idx, f
     else launch_prep_mlp(v, e->PL, e->prep_tan, e->stream);
     e->launches += 1;
     const long long n = idx ? n_idx : e->n_roll;
-    cudaEventRecord(e->ev[4], e->stream);
+    const int slot = (int)(e->fvp_count % mjb_engine::kFvpRing);
+    // the memset of the gradient partials belongs to the FVP; the event pair brackets memset + tile kernel
+    cudaEventRecord(e->fvp_ev[slot][0], e->stream);
     int grid = run_policy(e, MODE_FVP, e->pnew, e->prep_tan, n, idx, nullptr, 0);
     if (grid < 0) return -1;
-    cudaEventRecord(e->ev[5], e->stream);
+    cudaEventRecord(e->fvp_ev[slot][1], e->stream);
+    e->fvp_count += 1;
     launch_reduce_partials(e->gpartial, grid, e->gstride, e->d, e->dsc + (idx ? DS_SCALE_SUB : DS_SCALE), out,
                            e->pnew.theta, v, e->tLS, 1, e->stream);
     e->launches += 1;
@@ -362,6 +369,8 @@ void mjb_destroy(mjb_engine* e) {
     if (e->pinned) cudaFreeHost(e->pinned);
     if (e->h_dsc) cudaFreeHost(e->h_dsc);
     for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : e->user_ev) if (ev) cudaEventDestroy(ev);
+    for (auto& pr : e->fvp_ev) for (auto& ev : pr) if (ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -372,6 +381,8 @@ int mjb_create(const mjb_config* cfg, mjb_engine** out) {
     mjb_engine* e = new mjb_engine();
     e->cfg = *cfg;
     for (auto& ev : e->ev) ev = nullptr;
+    for (auto& ev : e->user_ev) ev = nullptr;
+    for (auto& pr : e->fvp_ev) for (auto& ev : pr) ev = nullptr;
     auto fail = [&](const std::string& m) { g_create_error = m.empty() ? e->err : m; mjb_destroy(e); return -1; };
     if (cfg->obs_dim < 1 || cfg->act_dim < 1 || cfg->act_dim > 32) return fail("act_dim must be in [1,32], obs_dim >= 1");
     if (cfg->n_hidden != 0 && cfg->n_hidden != 2) return fail("only 0 (linear) or 2 hidden layers are supported");
@@ -387,6 +398,8 @@ int mjb_create(const mjb_config* cfg, mjb_engine** out) {
     e->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("stream create failed");
     for (auto& ev : e->ev) if (cudaEventCreate(&ev) != cudaSuccess) return fail("event create failed");
+    for (auto& ev : e->user_ev) if (cudaEventCreate(&ev) != cudaSuccess) return fail("event create failed");
+    for (auto& pr : e->fvp_ev) for (auto& ev : pr) if (cudaEventCreate(&ev) != cudaSuccess) return fail("event create failed");
 
     e->linear = cfg->n_hidden == 0;
     e->A = cfg->act_dim;
@@ -569,7 +582,25 @@ int mjb_batch_set_advantages(mjb_engine* e, const double* adv_concat) {
     return 0;
 }
 
-int64_t mjb_batch_size(const mjb_engine* e, int which) { return which == MJB_BATCH_DEMO ? e->n_demo : e->n_roll; }
+int mjb_batch_set_adv_white(mjb_engine* e, const float* adv_white) {
+    CK(e, cudaMemcpyAsync(e->adv_white, adv_white, sizeof(float) * e->n_roll, cudaMemcpyDefault, e->stream));
+    e->have_white = true;
+    return 0;
+}
+
+int mjb_batch_set_baseline(mjb_engine* e, const float* base_concat) {
+    CK(e, cudaMemcpyAsync(e->base, base_concat, sizeof(float) * e->n_roll, cudaMemcpyDefault, e->stream));
+    return 0;
+}
+
+int mjb_batch_set_returns(mjb_engine* e, const double* ret_concat) {
+    CK(e, cudaMemcpyAsync(e->ret, ret_concat, sizeof(double) * e->n_roll, cudaMemcpyDefault, e->stream));
+    return 0;
+}
+
+int64_t mjb_batch_size(const mjb_engine* e, int which) {
+    return which == 2 ? e->n_glob_roll : (which == MJB_BATCH_DEMO ? e->n_demo : e->n_roll);
+}
 
 // ------------------------------------------------------------------------------- returns / advantages
 int mjb_compute_returns(mjb_engine* e, double gamma) {
@@ -722,9 +753,10 @@ int mjb_policy_fvp(mjb_engine* e, const float* v, float damping, const int32_t* 
     CK(e, cudaMemcpyAsync(e->dsc + DS_ALPHA, e->h_dsc + DS_ALPHA, sizeof(double), cudaMemcpyHostToDevice, e->stream));
     launch_axpy_clamp(e->Fp, e->tmpv, e->dsc + DS_ALPHA, 1.0, e->d, 0, 0.0f, e->Fp, e->stream);
     e->launches += 1;
-    cudaEventSynchronize(e->ev[5]);
-    cudaEventElapsedTime(&e->last_fvp_ms, e->ev[4], e->ev[5]);
-    return d2any(e, out, e->Fp, sizeof(float) * e->d);
+    if (d2any(e, out, e->Fp, sizeof(float) * e->d)) return -1;
+    const int slot = (int)((e->fvp_count - 1) % mjb_engine::kFvpRing);
+    cudaEventElapsedTime(&e->last_fvp_ms, e->fvp_ev[slot][0], e->fvp_ev[slot][1]);
+    return 0;
 }
 
 int mjb_policy_cg(mjb_engine* e, const float* b, int iters, float damping, float residual_tol, const int32_t* idx,
@@ -746,6 +778,7 @@ int mjb_policy_step(mjb_engine* e, int algo, double step_size_or_kl, double cons
     if (algo < MJB_ALGO_NPG || algo > MJB_ALGO_DAPG) FAIL(e, "bad algo");
     mjb_step_stats st;
     memset(&st, 0, sizeof(st));
+    const long long fvp0 = e->fvp_count;
     CK(e, cudaEventRecord(e->ev[0], e->stream));
     if (vpg_device(e, algo == MJB_ALGO_DAPG, demo_lam, &st.surr_before)) return -1;
     CK(e, cudaEventRecord(e->ev[1], e->stream));
@@ -809,7 +842,14 @@ int mjb_policy_step(mjb_engine* e, int algo, double step_size_or_kl, double cons
     cudaEventElapsedTime(&st.time_vpg_ms, e->ev[0], e->ev[1]);
     cudaEventElapsedTime(&st.time_npg_ms, e->ev[1], e->ev[2]);
     cudaEventElapsedTime(&st.time_eval_ms, e->ev[2], e->ev[3]);
-    cudaEventElapsedTime(&e->last_fvp_ms, e->ev[4], e->ev[5]);
+    for (long long k = std::max(fvp0, e->fvp_count - mjb_engine::kFvpRing); k < e->fvp_count; ++k) {
+        float ms = 0.f;
+        const int slot = (int)(k % mjb_engine::kFvpRing);
+        cudaEventElapsedTime(&ms, e->fvp_ev[slot][0], e->fvp_ev[slot][1]);
+        st.fvp_kernel_ms_sum += ms;
+        st.fvp_launches += 1;
+        e->last_fvp_ms = ms;
+    }
     if (out) *out = st;
     return 0;
 }
@@ -913,6 +953,17 @@ int mjb_vf_fit(mjb_engine* e, const int32_t* perms, int epochs, int batch_size, 
     return 0;
 }
 
+int mjb_event_record(mjb_engine* e, int slot) {
+    if (slot < 0 || slot >= 8) FAIL(e, "event slot out of range");
+    CK(e, cudaEventRecord(e->user_ev[slot], e->stream));
+    return 0;
+}
+int mjb_event_elapsed_ms(mjb_engine* e, int slot_a, int slot_b, float* ms) {
+    if (slot_a < 0 || slot_a >= 8 || slot_b < 0 || slot_b >= 8) FAIL(e, "event slot out of range");
+    CK(e, cudaEventSynchronize(e->user_ev[slot_b]));
+    CK(e, cudaEventElapsedTime(ms, e->user_ev[slot_a], e->user_ev[slot_b]));
+    return 0;
+}
 int64_t mjb_kernel_launches(const mjb_engine* e) { return e->launches; }
 int mjb_fvp_timing(mjb_engine* e, float* last_ms) { *last_ms = e->last_fvp_ms; return 0; }
 

@@ -128,6 +128,24 @@ class Engine:
         assert a.shape[0] == self.n
         self._ck(self.lib.mjb_batch_set_advantages(self.h, _ptr(a)), "set_advantages")
 
+    def set_white(self, adv_white):
+        w = _f32(adv_white)
+        assert w.shape[0] == self.n
+        self._ck(self.lib.mjb_batch_set_adv_white(self.h, _ptr(w)), "set_adv_white")
+
+    def set_returns(self, ret_concat):
+        r = np.ascontiguousarray(ret_concat, dtype=np.float64)
+        assert r.shape[0] == self.n
+        self._ck(self.lib.mjb_batch_set_returns(self.h, _ptr(r)), "set_returns")
+
+    def n_global(self):
+        return int(self.lib.mjb_batch_size(self.h, 2))
+
+    def set_baseline(self, base_concat):
+        b = _f32(base_concat)
+        assert b.shape[0] == self.n
+        self._ck(self.lib.mjb_batch_set_baseline(self.h, _ptr(b)), "set_baseline")
+
     # ------------------------------------------------------------------ returns / advantages
     def compute_returns(self, gamma):
         self._ck(self.lib.mjb_compute_returns(self.h, float(gamma)), "compute_returns")
@@ -241,6 +259,14 @@ class Engine:
         return (err[0], err[1]) if return_errors else None
 
     # ------------------------------------------------------------------ introspection
+    def event_record(self, slot):
+        self._ck(self.lib.mjb_event_record(self.h, int(slot)), "event_record")
+
+    def event_elapsed_ms(self, a, b):
+        t = C.c_float()
+        self._ck(self.lib.mjb_event_elapsed_ms(self.h, int(a), int(b), C.byref(t)), "event_elapsed")
+        return float(t.value)
+
     def kernel_launches(self):
         return int(self.lib.mjb_kernel_launches(self.h))
 

@@ -1,0 +1,81 @@
+"""Engine registry: one CUDA engine per (policy shape, baseline shape) in this process / on this rank.
+
+The reference has no such object -- its policy, baseline and agent talk through numpy arrays on the host.
+Here they share one device-resident engine so a rollout batch is uploaded once per train_step."""
+import os
+
+from mjrl_b200.engine import Engine
+
+_engines = {}
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(), dist.get_rank()
+    except Exception:
+        pass
+    return 1, 0
+
+
+def get_engine(obs_dim, act_dim, hidden=None, vf_hidden=(128, 128), min_log_std=-3.0, need_samples=0, need_paths=0):
+    """Return (creating or growing as needed) the engine for this shape.  hidden=None matches any policy
+    shape with the same obs/act dims (used by stand-alone baselines / process_samples calls)."""
+    world, rank = _dist()
+    device = int(os.environ.get("LOCAL_RANK", "0")) if world > 1 else int(os.environ.get("MJRL_B200_DEVICE", "0"))
+    key = None
+    if hidden is None:
+        for k in _engines:
+            if k[0] == obs_dim and k[1] == act_dim and k[3] == tuple(vf_hidden):
+                key = k
+                break
+        if key is None:
+            hidden = ()
+    if key is None:
+        key = (obs_dim, act_dim, tuple(hidden), tuple(vf_hidden), float(min_log_std))
+    eng = _engines.get(key)
+    if eng is not None and (need_samples > eng.max_samples or need_paths > eng.max_paths):
+        state = (eng.get_params(), eng.get_params(old=True), eng.vf_get_state())
+        eng.close()
+        eng = None
+    else:
+        state = None
+    if eng is None:
+        cap = max(1 << 14, int(need_samples * 1.25) + 64)
+        pcap = max(256, int(need_paths * 1.25) + 8)
+        eng = Engine(key[0], key[1], key[2], key[3], key[4], max_samples=cap, max_paths=pcap, device=device,
+                     world_size=world, rank=rank)
+        eng.init_comm()
+        eng.resident = None
+        if state is not None:
+            eng.set_params(state[0], True, False)
+            eng.set_params(state[1], False, True)
+            w, m, v, step = state[2]
+            eng.vf_set_state(w, m, v, step)
+        _engines[key] = eng
+    return eng
+
+
+def fingerprint(paths):
+    if len(paths) == 0:
+        return None
+    a, b = paths[0], paths[-1]
+    return (id(paths), len(paths), id(a["observations"]), id(b["observations"]), len(b["observations"]))
+
+
+def ensure_resident(eng, paths, force=False):
+    """Upload `paths` unless exactly this list is already the engine's rollout batch."""
+    fp = fingerprint(paths)
+    if force or getattr(eng, "resident", None) != fp:
+        eng.upload_paths(paths)
+        eng.resident = fp
+        eng.have_returns = False
+        eng.adv_paths = None
+    return eng
+
+
+def shutdown():
+    for e in _engines.values():
+        e.close()
+    _engines.clear()

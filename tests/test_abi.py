@@ -1,0 +1,78 @@
+"""CPU tests of the boundary: the shared library loads here (no GPU) and exports exactly the symbols
+include/mjrl_b200.h declares; creating an engine without a device fails loudly (no CPU fallback)."""
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "mjrl_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mjb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__
+    __graft_entry__.build()
+    from mjrl_b200 import _native
+    lib = _native.load()
+    declared = header_symbols()
+    assert declared == _native.exported_symbols()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.mjb_version() == 1
+
+
+def test_header_cites_reference():
+    src = open(os.path.join(ROOT, "include", "mjrl_b200.h")).read()
+    for cite in ("utils/process_samples.py", "algos/npg_cg.py", "utils/cg_solve.py", "baselines/mlp_baseline.py",
+                 "algos/trpo.py", "algos/dapg.py", "policies/gaussian_mlp.py"):
+        assert cite in src
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this check is for the CPU-only container")
+    from mjrl_b200.engine import Engine, MjbError
+    with pytest.raises(MjbError):
+        Engine(4, 2, (32, 32))
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under mjrl_b200/ may import it."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "mjrl_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("# oracle", ""), os.path.join(dirpath, f)
+
+
+def test_host_classes_construct_on_cpu():
+    import numpy as np
+    from mjrl_b200.algos.dapg import DAPG
+    from mjrl_b200.algos.npg_cg import NPG
+    from mjrl_b200.algos.trpo import TRPO
+    from mjrl_b200.baselines.mlp_baseline import MLPBaseline
+    from mjrl_b200.policies.gaussian_linear import LinearPolicy
+    from mjrl_b200.policies.gaussian_mlp import MLP
+    from mjrl_b200.utils.cg_solve import cg_solve
+    from mjrl_b200.utils.gym_env import EnvSpec
+    es = EnvSpec(6, 2, 50)
+    pol = MLP(es, hidden_sizes=(32, 32), seed=500)
+    assert pol.d == 1348 and LinearPolicy(EnvSpec(376, 17, 10), seed=0).d == 6426
+    th = pol.get_param_values()
+    th[-2:] = -7.0
+    pol.set_param_values(th)
+    assert np.all(pol.get_param_values()[-2:] == -3.0)          # min_log_std clamp (gaussian_mlp.py:73-75)
+    bl = MLPBaseline(es)
+    feat = bl._features([dict(observations=np.array([[0.0, 20, -30, 0, 0, 0], [1, 2, 3, 0, 0, 0]]), rewards=np.zeros(2))])
+    assert np.allclose(feat[1, -4:], [1e-3, 1e-6, 1e-9, 1e-12]) and feat[0, 1] == 1.0 and feat[0, 2] == -1.0
+    for cls, kw in ((NPG, {}), (TRPO, {}), (DAPG, dict(demo_paths=None))):
+        a = cls(None, pol, bl, **kw)
+        assert a.FIM_invert_args == {'iters': 10, 'damping': 1e-4}
+    A = np.array([[4.0, 1.0], [1.0, 3.0]])
+    assert np.allclose(cg_solve(lambda v: A.dot(v), np.array([1.0, 2.0]), cg_iters=2), [1 / 11, 7 / 11])

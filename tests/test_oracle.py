@@ -148,6 +148,16 @@ def test_golden_baseline_fit(case):
     np.testing.assert_allclose(pred, g["fit2_predict"], rtol=0, atol=1e-4)
 
 
+def test_fit_torch_flavour_equals_explicit_adam():
+    g = load_golden("swim_40x250")
+    paths = golden_paths(g)
+    O.compute_returns(paths, g["meta"]["gamma"])
+    a, b = vf_of(g), vf_of(g)
+    O.vf_fit(a, paths, list(g["fit_perms"][:1]), 1, 64, 1e-3, 1e-3)
+    O.vf_fit_torch(b, paths, list(g["fit_perms"][:1]), 1, 64, 1e-3, 1e-3)
+    assert a.t == b.t and rel(a.w, b.w) < 1e-5
+
+
 def test_fit_needs_two_batches():
     paths = O.synthetic_paths(3, 1, 2, 50, seed=0)
     O.compute_returns(paths, 0.9)
