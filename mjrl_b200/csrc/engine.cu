@@ -100,6 +100,7 @@ struct mjb_engine {
     int vfH = 0; PrepLayout VPL; int vf_d = 0;
     float *vf_w = nullptr, *vf_m = nullptr, *vf_v = nullptr, *vf_wT = nullptr, *vf_prep = nullptr;
     long long vf_step = 0;
+    float* vf_cl_scratch = nullptr; int vf_cluster = 8;     // cluster size of the fit kernel (0 = single-CTA kernel)
     int* perm_dev = nullptr; long long perm_cap = 0;
     // global (all-rank) copies used by the replicated fit when world_size > 1
     float* fit_obs = nullptr; int* fit_tstep = nullptr; double* fit_ret = nullptr; long long fit_cap = 0;
@@ -364,7 +365,7 @@ void mjb_destroy(mjb_engine* e) {
                     e->prep_tan, e->obs, e->act, e->rew, e->path_off, e->term, e->tstep, e->ret, e->adv, e->base,
                     e->adv_white, e->weights, e->path_ret, e->ll_old, e->mu_old, e->gpartial, e->eval_partial,
                     e->mom_scratch, e->dsc, e->g, e->x, e->r, e->p, e->Fp, e->tmpv, e->idx_dev, e->stage64, e->vf_w,
-                    e->vf_m, e->vf_v, e->vf_wT, e->vf_prep, e->perm_dev, e->fit_obs, e->fit_tstep, e->fit_ret};
+                    e->vf_m, e->vf_v, e->vf_wT, e->vf_prep, e->vf_cl_scratch, e->perm_dev, e->fit_obs, e->fit_tstep, e->fit_ret};
     for (void* b : bufs) if (b) cudaFree(b);
     if (e->pinned) cudaFreeHost(e->pinned);
     if (e->h_dsc) cudaFreeHost(e->h_dsc);
@@ -604,7 +605,7 @@ int64_t mjb_batch_size(const mjb_engine* e, int which) {
 
 // ------------------------------------------------------------------------------- returns / advantages
 int mjb_compute_returns(mjb_engine* e, double gamma) {
-    launch_returns(e->rew, e->path_off, e->n_paths, gamma, e->ret, e->path_ret, e->stream);
+    launch_returns(e->rew, e->path_off, e->n_paths, gamma, e->ret, e->stream);
     e->launches += 1;
     CK(e, cudaGetLastError());
     return 0;
@@ -668,6 +669,8 @@ int mjb_process_paths(mjb_engine* e, mjb_batch_stats* out) {
     e->launches += 5;
     e->have_white = true;
     // path-return statistics (batch_reinforce.py:188-192)
+    launch_path_sums(e->rew, e->path_off, e->n_paths, e->path_ret, e->stream);
+    e->launches += 1;
     std::vector<double> pr((size_t)std::max(1, e->n_paths));
     CK(e, cudaMemcpyAsync(pr.data(), e->path_ret, sizeof(double) * e->n_paths, cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
@@ -940,7 +943,15 @@ int mjb_vf_fit(mjb_engine* e, const int32_t* perms, int epochs, int batch_size, 
         a.obs = fobs; a.tstep = ftstep; a.returns = fret; a.n = N; a.perm = e->perm_dev;
         a.steps = steps; a.batch = batch_size; a.lr = lr; a.reg = reg_coef; a.beta1 = 0.9f; a.beta2 = 0.999f; a.eps = 1e-8f;
         a.step0 = e->vf_step; a.w = e->vf_w; a.m = e->vf_m; a.v = e->vf_v; a.wT = e->vf_wT; a.loss_out = nullptr;
-        cudaError_t ce = launch_vf_fit(a, e->stream);
+        cudaError_t ce;
+        if (e->vf_cluster > 0 && vf_cluster_supported(a.K, a.H1, a.H2, a.batch, e->vf_cluster)) {
+            if (!e->vf_cl_scratch)
+                CK(e, cudaMalloc(&e->vf_cl_scratch, sizeof(float) * vf_cluster_scratch_floats(a.K, a.H1, a.H2, 16)));
+            ce = launch_vf_fit_cluster(a, e->vf_cl_scratch, e->vf_cluster, e->stream);
+            e->launches += 2;
+        } else {
+            ce = launch_vf_fit(a, e->stream);
+        }
         if (ce != cudaSuccess) FAIL(e, std::string("vf fit launch (batch<=64, multiple of 4; sizes must fit 220 KB smem): ") + cudaGetErrorString(ce));
         e->launches += 1;
         e->vf_step += steps;
@@ -962,6 +973,11 @@ int mjb_event_elapsed_ms(mjb_engine* e, int slot_a, int slot_b, float* ms) {
     if (slot_a < 0 || slot_a >= 8 || slot_b < 0 || slot_b >= 8) FAIL(e, "event slot out of range");
     CK(e, cudaEventSynchronize(e->user_ev[slot_b]));
     CK(e, cudaEventElapsedTime(ms, e->user_ev[slot_a], e->user_ev[slot_b]));
+    return 0;
+}
+int mjb_vf_set_cluster(mjb_engine* e, int cluster_ctas) {
+    if (cluster_ctas != 0 && cluster_ctas != 8 && cluster_ctas != 16) FAIL(e, "cluster size must be 0, 8 or 16");
+    e->vf_cluster = cluster_ctas;
     return 0;
 }
 int64_t mjb_kernel_launches(const mjb_engine* e) { return e->launches; }

@@ -51,8 +51,8 @@ cudaError_t launch_linear(int mode, const LinArgs& args, int grid, cudaStream_t 
 // ---- scan.cu : returns / GAE / whitening / packing helpers
 void launch_f64_to_f32(const double* src, float* dst, long long n, cudaStream_t s);
 void launch_tstep(const int* path_off, int n_paths, int* tstep, cudaStream_t s);
-void launch_returns(const double* rew, const int* path_off, int n_paths, double gamma, double* ret,
-                    double* path_ret, cudaStream_t s);
+void launch_returns(const double* rew, const int* path_off, int n_paths, double gamma, double* ret, cudaStream_t s);
+void launch_path_sums(const double* rew, const int* path_off, int n_paths, double* path_ret, cudaStream_t s);
 void launch_advantages(const double* rew, const float* base, const double* ret, const int* path_off,
                        const unsigned char* terminated, int n_paths, double gamma, double gamma_lam,
                        int use_gae, double* adv, cudaStream_t s);
@@ -96,6 +96,10 @@ struct VfFitArgs {
     float* loss_out;                  // [steps] (optional)
 };
 cudaError_t launch_vf_fit(const VfFitArgs& a, cudaStream_t s);
+// vf_fit_cluster.cu : same chain on a thread-block cluster (minibatch split over C CTAs)
+size_t vf_cluster_scratch_floats(int K, int H1, int H2, int C);
+bool vf_cluster_supported(int K, int H1, int H2, int batch, int C);
+cudaError_t launch_vf_fit_cluster(const VfFitArgs& a, float* scratch, int C, cudaStream_t s);
 // err = sum((ret - pred)^2) / (sum(ret^2) + 1e-8) pieces: out = {sum err^2, sum ret^2} (fp32 casts like the reference)
 void launch_vf_error(const double* ret, const float* pred, long long n, double* scratch, double* out2, cudaStream_t s);
 

@@ -32,9 +32,9 @@ void launch_tstep(const int* path_off, int n_paths, int* tstep, cudaStream_t s) 
     tstep_kernel<<<min(n_paths, 148 * 8), 128, 0, s>>>(path_off, n_paths, tstep);
 }
 
-// returns (reverse scan) + per-path undiscounted return (forward sum, Python's sum() order)
+// returns: reverse scan y_t = r_t + gamma*y_{t+1}
 __global__ void returns_kernel(const double* __restrict__ rew, const int* __restrict__ path_off, int n_paths,
-                               double gamma, double* __restrict__ ret, double* __restrict__ path_ret) {
+                               double gamma, double* __restrict__ ret) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_paths) return;
     const int o = path_off[p], T = path_off[p + 1] - o;
@@ -43,14 +43,25 @@ __global__ void returns_kernel(const double* __restrict__ rew, const int* __rest
         run = __dadd_rn(rew[o + t], __dmul_rn(gamma, run));
         ret[o + t] = run;
     }
+}
+void launch_returns(const double* rew, const int* path_off, int n_paths, double gamma, double* ret, cudaStream_t s) {
+    if (n_paths <= 0) return;
+    returns_kernel<<<(n_paths + 31) / 32, 32, 0, s>>>(rew, path_off, n_paths, gamma, ret);
+}
+
+// per-path undiscounted return: forward sum in Python's sum() order (batch_reinforce.py:188)
+__global__ void path_sums_kernel(const double* __restrict__ rew, const int* __restrict__ path_off, int n_paths,
+                                 double* __restrict__ path_ret) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_paths) return;
+    const int o = path_off[p], T = path_off[p + 1] - o;
     double tot = 0.0;
     for (int t = 0; t < T; ++t) tot = __dadd_rn(tot, rew[o + t]);
     path_ret[p] = tot;
 }
-void launch_returns(const double* rew, const int* path_off, int n_paths, double gamma, double* ret,
-                    double* path_ret, cudaStream_t s) {
+void launch_path_sums(const double* rew, const int* path_off, int n_paths, double* path_ret, cudaStream_t s) {
     if (n_paths <= 0) return;
-    returns_kernel<<<(n_paths + 31) / 32, 32, 0, s>>>(rew, path_off, n_paths, gamma, ret, path_ret);
+    path_sums_kernel<<<(n_paths + 31) / 32, 32, 0, s>>>(rew, path_off, n_paths, path_ret);
 }
 
 __global__ void advantages_kernel(const double* __restrict__ rew, const float* __restrict__ base,

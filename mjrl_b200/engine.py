@@ -258,6 +258,9 @@ class Engine:
                                      C.byref(err) if return_errors else None), "vf_fit")
         return (err[0], err[1]) if return_errors else None
 
+    def vf_set_cluster(self, ctas):
+        self._ck(self.lib.mjb_vf_set_cluster(self.h, int(ctas)), "vf_set_cluster")
+
     # ------------------------------------------------------------------ introspection
     def event_record(self, slot):
         self._ck(self.lib.mjb_event_record(self.h, int(slot)), "event_record")

@@ -138,11 +138,14 @@ def test_policy_steps(case, cuda_device):
     eng.close()
 
 
+@pytest.mark.parametrize("cluster", [8, 16, 0])
 @pytest.mark.parametrize("case", ["pm_5x50", "pm_40x25_ragged", "swim_40x250", "linear_30x200"])
-def test_baseline_fit(case, cuda_device):
+def test_baseline_fit(case, cluster, cuda_device):
+    """cluster = CTAs of the thread-block cluster running the sequential Adam chain (0 = single-CTA kernel)."""
     g = load_golden(case)
     paths = golden_paths(g)
     eng = make_engine(g, cuda_device)
+    eng.vf_set_cluster(cluster)
     eng.upload_paths(paths)
     eng.compute_returns(g["meta"]["gamma"])
     err = eng.vf_fit(g["fit_perms"][:2], 64, 1e-3, 1e-3, return_errors=True)
