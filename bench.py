@@ -24,8 +24,11 @@ import sys
 import threading
 import time
 
+import faulthandler
+
 import numpy as np
 
+faulthandler.enable()
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -233,6 +236,7 @@ def run_gpu(args, cfg, rank, world, local_rank):
     kw = dict(FIM_invert_args={"iters": CG_ITERS, "damping": DAMPING}, save_logs=False)
     if cfg["algo"] == "trpo":
         agent = TRPO(None, pol, bl, kl_dist=KL_DIST, **kw)
+        agent.verbose = False            # the reference prints one line per backtrack; stdout carries the JSON line here
     elif cfg["algo"] == "dapg":
         agent = DAPG(None, pol, bl, demo_paths=demo, kl_dist=KL_DIST, **kw)
     else:

@@ -18,6 +18,7 @@ class TRPO(NPG):
         return dict(step_size=self.kl_dist)
 
     def _finish_step(self, eng, st, paths, t_host):
-        for _ in range(st.backtracks):          # the reference prints once per shrink (trpo.py:117-118)
-            print("Step size too high. Backtracking.")
+        if getattr(self, "verbose", True):
+            for _ in range(st.backtracks):      # the reference prints once per shrink (trpo.py:117-118)
+                print("Step size too high. Backtracking.")
         super()._finish_step(eng, st, paths, t_host)

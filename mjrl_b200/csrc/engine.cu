@@ -975,6 +975,17 @@ int mjb_event_elapsed_ms(mjb_engine* e, int slot_a, int slot_b, float* ms) {
     CK(e, cudaEventElapsedTime(ms, e->user_ev[slot_a], e->user_ev[slot_b]));
     return 0;
 }
+// Developer aid (not part of the public header): per-phase clock64 cycle counters of the cluster fit kernel.
+int mjb_dev_vf_profile(mjb_engine* e, long long* out16, int enable) {
+    static long long* dev = nullptr;
+    if (!dev) { CK(e, cudaMalloc(&dev, 16 * sizeof(long long))); }
+    if (enable) { CK(e, cudaMemset(dev, 0, 16 * sizeof(long long))); vf_cluster_set_prof(dev); return 0; }
+    CK(e, cudaStreamSynchronize(e->stream));
+    CK(e, cudaMemcpy(out16, dev, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+    vf_cluster_set_prof(nullptr);
+    return 0;
+}
+
 int mjb_vf_set_cluster(mjb_engine* e, int cluster_ctas) {
     if (cluster_ctas != 0 && cluster_ctas != 8 && cluster_ctas != 16) FAIL(e, "cluster size must be 0, 8 or 16");
     e->vf_cluster = cluster_ctas;
