@@ -181,11 +181,14 @@ __global__ void __launch_bounds__(CT, 1) vf_fit_cluster_kernel(const ClArgs a) {
 
     // k-split GEMV helper: partial[t] = sum_{r in my range} in[r][0..7] * w(r), stored to red[t*8..]
     // thread t -> (o = t % NO: output unit, ks = t / NO: reduction slice)
+    float2 cc_next = make_float2(1.f, 0.f);
+    if (tid == 0) cc_next = a.consts[0];
     long long t_last = clock64();
 #define MJB_PROF(i) do { if (a.prof && tid == 0 && c == 0) { const long long _t = clock64(); a.prof[i] += _t - t_last; t_last = _t; } } while (0)
     for (int s = 0; s < a.steps; ++s) {
         if (tid == 0) {
-            const float2 cc = a.consts[s];
+            const float2 cc = cc_next;
+            if (s + 1 < a.steps) cc_next = a.consts[s + 1];   // consumed next step: off the critical path
             s_c.one_m_b1 = (float)(1.0 - (double)a.beta1);
             s_c.b2 = a.beta2;
             s_c.one_m_b2 = (float)(1.0 - (double)a.beta2);

@@ -75,16 +75,11 @@ class Engine:
         """Create the engine-owned NCCL communicator; the unique id travels over torch.distributed."""
         if self.world_size == 1:
             return
-        import torch
-        import torch.distributed as dist
+        from .parallel import broadcast_bytes
         buf = (C.c_char * 128)()
         if self.rank == 0 and self.lib.mjb_comm_unique_id(buf) != 0:
             raise MjbError("mjb_comm_unique_id: " + self.lib.mjb_last_error(None).decode())
-        t = torch.frombuffer(bytearray(bytes(buf)), dtype=torch.uint8).clone()
-        if dist.get_backend() == "nccl":
-            t = t.cuda(self.cfg.device)
-        dist.broadcast(t, src=0)
-        raw = bytes(t.cpu().numpy().tobytes())
+        raw = broadcast_bytes(bytes(buf), 128, src=0, device=self.cfg.device)
         self._ck(self.lib.mjb_comm_init(self.h, C.c_char_p(raw)), "comm_init")
 
     # ------------------------------------------------------------------ trajectories

@@ -1,0 +1,73 @@
+"""Run under torchrun (one rank per GPU): shard-invariance of the engine.  Every rank holds a contiguous shard
+of the golden trajectories; the all-reduced results must equal the single-GPU / reference values.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/multigpu_check.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from conftest import golden_paths, load_golden, one_minus_cos, rel  # noqa: E402
+from mjrl_b200.engine import Engine  # noqa: E402
+from mjrl_b200.parallel import shard_bounds  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    for case in ("swim_40x250", "cheetah_24x500", "linear_30x200"):
+        g = load_golden(case)
+        m = g["meta"]
+        paths = golden_paths(g)
+        lens = [len(p["rewards"]) for p in paths]
+        b = shard_bounds(lens, world)
+        s, e = b[rank]
+        mine = paths[s:e]
+        off = int(np.sum(lens[:s]))
+        n_loc = int(np.sum(lens[s:e]))
+        eng = Engine(m["obs_dim"], m["act_dim"], m["hidden"], max_samples=n_loc + 8, max_paths=len(mine) + 1,
+                     device=local, world_size=world, rank=rank)
+        eng.init_comm()
+        eng.set_params(g["theta0"])
+        eng.vf_set_state(g["vf_w0"], np.zeros_like(g["vf_w0"]), np.zeros_like(g["vf_w0"]), 0)
+        eng.upload_paths(mine)
+        eng.compute_returns(m["gamma"])
+        assert np.array_equal(eng.returns(), g["returns"][off:off + n_loc])
+        eng.set_advantages(g["advantages"][off:off + n_loc])
+        st = eng.process_paths()
+        np.testing.assert_allclose([st.mean_return, st.std_return, st.min_return, st.max_return], g["base_stats"], rtol=1e-10)
+        np.testing.assert_allclose(eng.adv_white(), g["adv_white"][off:off + n_loc].astype(np.float32), atol=1e-6, rtol=0)
+        assert rel(eng.vpg(), g["vpg"]) < 1e-5
+        assert rel(eng.fvp(g["fvp_vec"], m["damping"]), g["fvp_out"]) < 1e-5
+        x = eng.cg(g["vpg"], iters=m["cg_iters"], damping=m["damping"])
+        assert one_minus_cos(x, g["cg_x"]) < 1e-6
+        st = eng.step("npg", step_size=m["npg_step"], cg_iters=m["cg_iters"], damping=m["damping"])
+        new = eng.get_params()
+        assert rel(new, g["npg_theta"]) < 1e-4, rel(new, g["npg_theta"])
+        assert abs(st.kl_dist / g["npg_kl_dist"] - 1) < 5e-3
+        # every rank ends with identical parameters
+        t = torch.from_numpy(new.copy()).cuda()
+        lo, hi = t.clone(), t.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert torch.equal(lo, hi)
+        if "fit_perms" in g and case != "cheetah_24x500":
+            err = eng.vf_fit(g["fit_perms"][:2], 64, 1e-3, 1e-3, return_errors=True)   # replicated sequential fit
+            np.testing.assert_allclose(err, g["fit1_err"], rtol=2e-4)
+            w = eng.vf_get_state()[0]
+            assert rel(w, g["fit1_w"]) < 1e-4
+        eng.close()
+        if rank == 0:
+            print("multigpu ok:", case, "world", world, flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
