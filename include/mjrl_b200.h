@@ -150,10 +150,12 @@ int  mjb_vf_get_state(mjb_engine* e, float* w, float* m, float* v, int64_t* step
 int  mjb_vf_fit(mjb_engine* e, const int32_t* perms, int epochs, int batch_size, float lr, float reg_coef,
                 double err_out[2]);
 
-/* Execution shape of the fit: 8 or 16 = thread-block cluster of that many CTAs (minibatch rows split over
- * the cluster, gradients exchanged through L2 between hardware cluster barriers); 0 = single-CTA kernel
- * (also the automatic fallback for shapes whose weights do not fit one CTA's shared memory). */
-int  mjb_vf_set_cluster(mjb_engine* e, int cluster_ctas);
+/* Execution shape of the fit.  cluster_ctas 8 or 16 = one thread-block cluster of that many CTAs:
+ *   model_parallel = 1 (default, 16 CTAs): hidden units split over the cluster -- weights and Adam moments stay in
+ *                      their owner's shared memory, activation slices cross distributed shared memory;
+ *   model_parallel = 0: minibatch rows split over the cluster, gradients exchanged through L2;
+ * cluster_ctas 0 = single-CTA kernel (also the automatic fallback for shapes the cluster kernels do not cover). */
+int  mjb_vf_set_cluster(mjb_engine* e, int cluster_ctas, int model_parallel);
 
 /* ---- introspection for benchmarks ------------------------------------------------------------ */
 /* CUDA events on the engine's stream (slots 0..7) so callers time on the device, not by wall clock. */

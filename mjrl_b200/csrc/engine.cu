@@ -100,7 +100,9 @@ struct mjb_engine {
     int vfH = 0; PrepLayout VPL; int vf_d = 0;
     float *vf_w = nullptr, *vf_m = nullptr, *vf_v = nullptr, *vf_wT = nullptr, *vf_prep = nullptr;
     long long vf_step = 0;
-    float* vf_cl_scratch = nullptr; int vf_cluster = 8;     // cluster size of the fit kernel (0 = single-CTA kernel)
+    float* vf_cl_scratch = nullptr;
+    int vf_cluster = 16;      // cluster size of the fit kernel (0 = single-CTA kernel)
+    int vf_model_parallel = 1; // 1: hidden units split over the cluster (vf_fit_mp.cu); 0: minibatch rows split (vf_fit_cluster.cu)
     int* perm_dev = nullptr; long long perm_cap = 0;
     // global (all-rank) copies used by the replicated fit when world_size > 1
     float* fit_obs = nullptr; int* fit_tstep = nullptr; double* fit_ret = nullptr; long long fit_cap = 0;
@@ -944,7 +946,10 @@ int mjb_vf_fit(mjb_engine* e, const int32_t* perms, int epochs, int batch_size, 
         a.steps = steps; a.batch = batch_size; a.lr = lr; a.reg = reg_coef; a.beta1 = 0.9f; a.beta2 = 0.999f; a.eps = 1e-8f;
         a.step0 = e->vf_step; a.w = e->vf_w; a.m = e->vf_m; a.v = e->vf_v; a.wT = e->vf_wT; a.loss_out = nullptr;
         cudaError_t ce;
-        if (e->vf_cluster > 0 && vf_cluster_supported(a.K, a.H1, a.H2, a.batch, e->vf_cluster)) {
+        if (e->vf_cluster > 0 && e->vf_model_parallel && vf_mp_supported(a.K, a.H1, a.H2, a.batch, e->vf_cluster)) {
+            ce = launch_vf_fit_mp(a, e->vf_cluster, e->stream);
+            e->launches += 2;
+        } else if (e->vf_cluster > 0 && vf_cluster_supported(a.K, a.H1, a.H2, a.batch, e->vf_cluster)) {
             if (!e->vf_cl_scratch)
                 CK(e, cudaMalloc(&e->vf_cl_scratch, sizeof(float) * vf_cluster_scratch_floats(a.K, a.H1, a.H2, 16)));
             ce = launch_vf_fit_cluster(a, e->vf_cl_scratch, e->vf_cluster, e->stream);
@@ -979,16 +984,17 @@ int mjb_event_elapsed_ms(mjb_engine* e, int slot_a, int slot_b, float* ms) {
 int mjb_dev_vf_profile(mjb_engine* e, long long* out16, int enable) {
     static long long* dev = nullptr;
     if (!dev) { CK(e, cudaMalloc(&dev, 16 * sizeof(long long))); }
-    if (enable) { CK(e, cudaMemset(dev, 0, 16 * sizeof(long long))); vf_cluster_set_prof(dev); return 0; }
+    if (enable) { CK(e, cudaMemset(dev, 0, 16 * sizeof(long long))); vf_cluster_set_prof(dev); vf_mp_set_prof(dev); return 0; }
     CK(e, cudaStreamSynchronize(e->stream));
     CK(e, cudaMemcpy(out16, dev, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
-    vf_cluster_set_prof(nullptr);
+    vf_cluster_set_prof(nullptr); vf_mp_set_prof(nullptr);
     return 0;
 }
 
-int mjb_vf_set_cluster(mjb_engine* e, int cluster_ctas) {
+int mjb_vf_set_cluster(mjb_engine* e, int cluster_ctas, int model_parallel) {
     if (cluster_ctas != 0 && cluster_ctas != 8 && cluster_ctas != 16) FAIL(e, "cluster size must be 0, 8 or 16");
     e->vf_cluster = cluster_ctas;
+    e->vf_model_parallel = model_parallel != 0;
     return 0;
 }
 int64_t mjb_kernel_launches(const mjb_engine* e) { return e->launches; }

@@ -101,6 +101,10 @@ size_t vf_cluster_scratch_floats(int K, int H1, int H2, int C);
 bool vf_cluster_supported(int K, int H1, int H2, int batch, int C);
 void vf_cluster_set_prof(long long* dev16);
 cudaError_t launch_vf_fit_cluster(const VfFitArgs& a, float* scratch, int C, cudaStream_t s);
+// vf_fit_mp.cu : same chain, hidden units split over the cluster (weights / Adam state stay put, DSMEM exchange)
+bool vf_mp_supported(int K, int H1, int H2, int batch, int C);
+void vf_mp_set_prof(long long* dev16);
+cudaError_t launch_vf_fit_mp(const VfFitArgs& a, int C, cudaStream_t s);
 // err = sum((ret - pred)^2) / (sum(ret^2) + 1e-8) pieces: out = {sum err^2, sum ret^2} (fp32 casts like the reference)
 void launch_vf_error(const double* ret, const float* pred, long long n, double* scratch, double* out2, cudaStream_t s);
 

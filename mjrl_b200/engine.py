@@ -253,8 +253,8 @@ class Engine:
                                      C.byref(err) if return_errors else None), "vf_fit")
         return (err[0], err[1]) if return_errors else None
 
-    def vf_set_cluster(self, ctas):
-        self._ck(self.lib.mjb_vf_set_cluster(self.h, int(ctas)), "vf_set_cluster")
+    def vf_set_cluster(self, ctas, model_parallel=True):
+        self._ck(self.lib.mjb_vf_set_cluster(self.h, int(ctas), int(model_parallel)), "vf_set_cluster")
 
     # ------------------------------------------------------------------ introspection
     def event_record(self, slot):

@@ -14,11 +14,14 @@ eng = Engine(obs_dim, 6, (128, 128), max_samples=N + 8, max_paths=256)
 eng.upload_flat(rng.randn(N, obs_dim), rng.randn(N, 6), rng.randn(N), np.full(200, 1000, np.int32), np.zeros(200, np.uint8))
 eng.compute_returns(0.995)
 w = (0.1 * rng.randn(eng.vf_d)).astype(np.float32)
-names = ["fwd L1", "fwd L2", "out+dy", "W3 grad+delta2", "dgrad+wgrad W2", "wgrad W1", "cluster sync 1", "reduce+adam",
-         "cluster sync 2", "reload+commit"]
-for cl in (8, 16):
+names_dp = ["fwd L1", "fwd L2", "out+dy", "W3 grad+delta2", "dgrad+wgrad W2", "wgrad W1", "cluster sync 1", "reduce+adam",
+            "cluster sync 2", "reload+commit"]
+names_mp = ["P1 L1 slice + E1 scatter", "cluster sync 1", "P2 L2 slice + E2", "cluster sync 2", "P3 delta2/dgrad scatter/wgrad",
+            "cluster sync 3", "P4 delta1 + P5 Adam", "-", "-", "-"]
+for cl, mp in ((16, True), (8, True), (8, False), (16, False)):
+    names = names_mp if mp else names_dp
     eng.vf_set_state(w, np.zeros_like(w), np.zeros_like(w), 0)
-    eng.vf_set_cluster(cl)
+    eng.vf_set_cluster(cl, mp)
     perm = rng.permutation(N).astype(np.int32)
     eng.vf_fit(perm, 64, 1e-3, 1e-3)
     eng.lib.mjb_dev_vf_profile(eng.h, None, 1)
@@ -29,6 +32,8 @@ for cl in (8, 16):
     eng.lib.mjb_dev_vf_profile(eng.h, out, 0)
     steps = N // 64 - 1
     tot = sum(out[:10])
-    print("cluster=%d: %.2f us/step wall, %d cycles/step" % (cl, dt / steps * 1e6, tot // steps))
+    print("cluster=%d model_parallel=%s: %.2f us/step wall, %d cycles/step" % (cl, mp, dt / steps * 1e6, tot // steps))
     for i, n in enumerate(names):
+        if n == "-":
+            continue
         print("   %-16s %7d cyc  %5.1f%%" % (n, out[i] // steps, 100.0 * out[i] / tot))
