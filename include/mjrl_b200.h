@@ -150,6 +150,12 @@ int  mjb_vf_get_state(mjb_engine* e, float* w, float* m, float* v, int64_t* step
 int  mjb_vf_fit(mjb_engine* e, const int32_t* perms, int epochs, int batch_size, float lr, float reg_coef,
                 double err_out[2]);
 
+/* The same fit, asynchronous: _begin launches the sequential chain on the engine's side stream (it only depends on
+ * the returns, so it can run concurrently with mjb_policy_step on the remaining SMs); _end joins, refreshes the
+ * predict weights and optionally evaluates error_after.  Any call that needs the baseline state joins implicitly. */
+int  mjb_vf_fit_begin(mjb_engine* e, const int32_t* perms, int epochs, int batch_size, float lr, float reg_coef,
+                      double* err_before);
+int  mjb_vf_fit_end(mjb_engine* e, double* err_after);
 /* Execution shape of the fit.  cluster_ctas 8 or 16 = one thread-block cluster of that many CTAs:
  *   model_parallel = 1 (default, 16 CTAs): hidden units split over the cluster -- weights and Adam moments stay in
  *                      their owner's shared memory, activation slices cross distributed shared memory;

@@ -75,6 +75,8 @@ _SIGNATURES = {
     "mjb_vf_set_state": (C.c_int, [_P, _P, _P, _P, C.c_int64]),
     "mjb_vf_get_state": (C.c_int, [_P, _P, _P, _P, C.POINTER(C.c_int64)]),
     "mjb_vf_fit": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_double * 2)]),
+    "mjb_vf_fit_begin": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_double)]),
+    "mjb_vf_fit_end": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "mjb_vf_set_cluster": (C.c_int, [_P, C.c_int, C.c_int]),
     "mjb_event_record": (C.c_int, [_P, C.c_int]),
     "mjb_event_elapsed_ms": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_float)]),

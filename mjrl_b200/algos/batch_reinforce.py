@@ -127,16 +127,30 @@ class BatchREINFORCE:
         eng = self._resident(paths)
         process_samples.returns_on(eng, paths, gamma)
         process_samples.advantages_on(eng, paths, self.baseline, gamma, gae_lambda)
+        overlap = hasattr(self.baseline, "fit_begin")
+        ts = timer.time()
+        if overlap:
+            # The sequential baseline fit depends only on the returns: start it now on the engine's side stream so it
+            # runs concurrently with the policy update.  Host RNG draws keep the reference's order (A9): the FVP
+            # subsample indices of this step first, then the fit permutations.
+            self._pending_hvp_idx = self._draw_hvp_indices(eng.n, self.FIM_invert_args['iters']) \
+                if hasattr(self, "_draw_hvp_indices") else None
+            self._hvp_idx_drawn = True
+            error_before = self.baseline.fit_begin(paths, return_errors=self.save_logs)
         eval_statistics = self.train_from_paths(paths)
         if self.save_logs:
             self.logger.log_kv('num_samples', int(np.sum([p["rewards"].shape[0] for p in paths])))
+        if overlap:
+            error_after = self.baseline.fit_end(return_errors=self.save_logs)
+        elif self.save_logs:
             ts = timer.time()
             error_before, error_after = self.baseline.fit(paths, return_errors=True)
+        else:
+            self.baseline.fit(paths)
+        if self.save_logs:
             self.logger.log_kv('time_VF', timer.time() - ts)
             self.logger.log_kv('VF_error_before', error_before)
             self.logger.log_kv('VF_error_after', error_after)
-        else:
-            self.baseline.fit(paths)
         return eval_statistics
 
     # ------------------------------------------------------------------ shared pieces of train_from_paths

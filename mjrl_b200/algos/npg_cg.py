@@ -76,7 +76,10 @@ class NPG(BatchREINFORCE):
             self._normalize_inputs(eng, paths)
         iters = self.FIM_invert_args['iters']
         demo_lam = self._demo_lam(eng)
-        idx = self._draw_hvp_indices(eng.n, iters)
+        if getattr(self, "_hvp_idx_drawn", False):          # drawn early by update_from_paths (RNG order, A9)
+            idx, self._hvp_idx_drawn = self._pending_hvp_idx, False
+        else:
+            idx = self._draw_hvp_indices(eng.n, iters)
         st = eng.step(self.algo, cg_iters=iters, damping=self.FIM_invert_args['damping'], demo_lam=demo_lam,
                       hvp_idx=idx, **self._step_args())
         self._finish_step(eng, st, paths, timer.time() - t0)

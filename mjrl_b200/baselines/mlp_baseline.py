@@ -93,6 +93,15 @@ class MLPBaseline:
         return feat
 
     def fit(self, paths, return_errors=False):
+        """mlp_baseline.py:61-95."""
+        e0 = self.fit_begin(paths, return_errors)
+        e1 = self.fit_end(return_errors)
+        if return_errors:
+            return e0, e1
+
+    def fit_begin(self, paths, return_errors=False):
+        """Launch the fit on the engine's side stream and return immediately (error_before if requested).  The chain
+        only needs the returns, so the agents start it before the policy update and join with fit_end() after."""
         n = int(sum(len(p["rewards"]) for p in paths))
         eng = self._eng(n, len(paths))
         runtime.ensure_resident(eng, paths)
@@ -103,10 +112,12 @@ class MLPBaseline:
         n_glob = eng.n_global()
         # host RNG draw at the reference's program point (optimize_model.py:22): one permutation per epoch
         perms = np.stack([np.random.permutation(n_glob) for _ in range(self.epochs)]).astype(np.int32)
-        out = eng.vf_fit(perms, self.batch_size, self.learn_rate, self.reg_coef, return_errors=return_errors)
+        return eng.vf_fit_begin(perms, self.batch_size, self.learn_rate, self.reg_coef, return_errors=return_errors)
+
+    def fit_end(self, return_errors=False):
+        err = self._engine.vf_fit_end(return_errors)
         self._pull()
-        if return_errors:
-            return out
+        return err
 
     def predict(self, path):
         eng = self._eng(len(path["rewards"]), 1)

@@ -44,6 +44,12 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
     return v;
 }
 
+// Cluster-wide barrier with release/acquire at CLUSTER scope (what distributed-shared-memory exchange needs).
+// cooperative_groups' cluster.sync() additionally emits a gpu-scope MEMBAR per call, which costs ~1-2k cycles.
+__device__ __forceinline__ void cluster_sync_relacq() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
 // Layout of a "prepped" (padded / transposed) parameter set of a 2-hidden-layer net, in floats.
 // All three kernels modes read the same layout for theta (new), theta_old and the CG tangent v.
 struct PrepLayout {

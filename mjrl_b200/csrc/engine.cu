@@ -63,6 +63,8 @@ struct mjb_engine {
     mjb_config cfg;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_vf = nullptr;      // side stream of the asynchronous baseline fit
+    bool fit_in_flight = false;
     std::string err;
     long long launches = 0;
     // ---- policy
@@ -101,6 +103,7 @@ struct mjb_engine {
     float *vf_w = nullptr, *vf_m = nullptr, *vf_v = nullptr, *vf_wT = nullptr, *vf_prep = nullptr;
     long long vf_step = 0;
     float* vf_cl_scratch = nullptr;
+    float* vf_feat = nullptr; float* vf_ret32 = nullptr; long long vf_feat_cap = 0;   // fp32 features / targets of the fit
     int vf_cluster = 16;      // cluster size of the fit kernel (0 = single-CTA kernel)
     int vf_model_parallel = 1; // 1: hidden units split over the cluster (vf_fit_mp.cu); 0: minibatch rows split (vf_fit_cluster.cu)
     int* perm_dev = nullptr; long long perm_cap = 0;
@@ -202,7 +205,9 @@ int run_policy(mjb_engine* e, int mode, const ParamSet& ps, const float* tangent
     }
     const int MT = e->linear ? 128 : mlp_tile_rows_for(e->H);
     const long long tiles = (n + MT - 1) / MT;
-    int grid = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)e->occ[mode] * e->num_sms));
+    // while the fit cluster is running on its own stream it owns vf_cluster SMs: size the persistent grid for the rest
+    const int sms = e->num_sms - (e->fit_in_flight ? std::max(e->vf_cluster, 1) : 0);
+    int grid = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)e->occ[mode] * sms));
     grid = std::min(grid, e->max_grid);
     if (bwd) CK(e, cudaMemsetAsync(e->gpartial, 0, sizeof(float) * (size_t)grid * e->gstride, e->stream));
     cudaError_t ce;
@@ -367,13 +372,14 @@ void mjb_destroy(mjb_engine* e) {
                     e->prep_tan, e->obs, e->act, e->rew, e->path_off, e->term, e->tstep, e->ret, e->adv, e->base,
                     e->adv_white, e->weights, e->path_ret, e->ll_old, e->mu_old, e->gpartial, e->eval_partial,
                     e->mom_scratch, e->dsc, e->g, e->x, e->r, e->p, e->Fp, e->tmpv, e->idx_dev, e->stage64, e->vf_w,
-                    e->vf_m, e->vf_v, e->vf_wT, e->vf_prep, e->vf_cl_scratch, e->perm_dev, e->fit_obs, e->fit_tstep, e->fit_ret};
+                    e->vf_m, e->vf_v, e->vf_wT, e->vf_prep, e->vf_cl_scratch, e->vf_feat, e->vf_ret32, e->perm_dev, e->fit_obs, e->fit_tstep, e->fit_ret};
     for (void* b : bufs) if (b) cudaFree(b);
     if (e->pinned) cudaFreeHost(e->pinned);
     if (e->h_dsc) cudaFreeHost(e->h_dsc);
     for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : e->user_ev) if (ev) cudaEventDestroy(ev);
     for (auto& pr : e->fvp_ev) for (auto& ev : pr) if (ev) cudaEventDestroy(ev);
+    if (e->stream_vf) { cudaStreamSynchronize(e->stream_vf); cudaStreamDestroy(e->stream_vf); }
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -400,6 +406,7 @@ int mjb_create(const mjb_config* cfg, mjb_engine** out) {
     if (prop.major < 10) return fail("mjrl_b200 kernels are built for sm_100a (Blackwell) only");
     e->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("stream create failed");
+    if (cudaStreamCreateWithFlags(&e->stream_vf, cudaStreamNonBlocking) != cudaSuccess) return fail("stream create failed");
     for (auto& ev : e->ev) if (cudaEventCreate(&ev) != cudaSuccess) return fail("event create failed");
     for (auto& ev : e->user_ev) if (cudaEventCreate(&ev) != cudaSuccess) return fail("event create failed");
     for (auto& pr : e->fvp_ev) for (auto& ev : pr) if (cudaEventCreate(&ev) != cudaSuccess) return fail("event create failed");
@@ -464,7 +471,11 @@ int mjb_create(const mjb_config* cfg, mjb_engine** out) {
     return 0;
 }
 
-int mjb_synchronize(mjb_engine* e) { CK(e, cudaStreamSynchronize(e->stream)); return 0; }
+int mjb_synchronize(mjb_engine* e) {
+    CK(e, cudaStreamSynchronize(e->stream));
+    if (e->fit_in_flight) CK(e, cudaStreamSynchronize(e->stream_vf));
+    return 0;
+}
 
 int mjb_comm_unique_id(void* id128) {
     std::string err;
@@ -486,6 +497,7 @@ int mjb_comm_init(mjb_engine* e, const void* id128) {
 }
 
 // ---------------------------------------------------------------------------------------------- batch
+int mjb_vf_fit_end(mjb_engine* e, double* err_after);
 static int finish_upload(mjb_engine* e, int which, int n_paths, const int32_t* len, const uint8_t* terminated, long long n) {
     if (which == MJB_BATCH_ROLLOUT) {
         e->h_path_off.assign((size_t)n_paths + 1, 0);
@@ -520,6 +532,7 @@ int mjb_batch_upload(mjb_engine* e, int which, int32_t n_paths, const double* co
                      const double* const* rew, const int32_t* len, const uint8_t* terminated) {
     if (which != MJB_BATCH_ROLLOUT && which != MJB_BATCH_DEMO) FAIL(e, "bad batch id");
     if (n_paths < 0 || (which == MJB_BATCH_ROLLOUT && n_paths > e->cfg.max_paths)) FAIL(e, "too many paths for max_paths");
+    if (e->fit_in_flight && mjb_vf_fit_end(e, nullptr)) return -1;
     long long n = 0;
     for (int i = 0; i < n_paths; ++i) { if (len[i] < 0) FAIL(e, "negative path length"); n += len[i]; }
     const long long row0 = which == MJB_BATCH_DEMO ? e->n_roll : 0;
@@ -565,6 +578,7 @@ int mjb_batch_upload_flat(mjb_engine* e, int which, int32_t n_paths, const doubl
                           const double* rew, const int32_t* len, const uint8_t* terminated) {
     if (which != MJB_BATCH_ROLLOUT && which != MJB_BATCH_DEMO) FAIL(e, "bad batch id");
     if (n_paths < 0 || (which == MJB_BATCH_ROLLOUT && n_paths > e->cfg.max_paths)) FAIL(e, "too many paths for max_paths");
+    if (e->fit_in_flight && mjb_vf_fit_end(e, nullptr)) return -1;
     long long n = 0;
     for (int i = 0; i < n_paths; ++i) n += len[i];
     const long long row0 = which == MJB_BATCH_DEMO ? e->n_roll : 0;
@@ -613,7 +627,10 @@ int mjb_compute_returns(mjb_engine* e, double gamma) {
     return 0;
 }
 
+int mjb_vf_fit_end(mjb_engine* e, double* err_after);
+
 int mjb_vf_predict(mjb_engine* e) {
+    if (e->fit_in_flight && mjb_vf_fit_end(e, nullptr)) return -1;
     if (e->occ[MODE_VF] == 0) {
         e->occ[MODE_VF] = occupancy_any(e->vfH, MODE_VF, e->VPL.YR);
         if (e->occ[MODE_VF] <= 0) FAIL(e, "vf kernel does not fit");
@@ -869,6 +886,7 @@ int mjb_policy_last_vectors(mjb_engine* e, float* vpg_out, float* npg_out) {
 int mjb_vf_dim(const mjb_engine* e) { return e->vf_d; }
 
 int mjb_vf_set_state(mjb_engine* e, const float* w, const float* m, const float* v, int64_t step) {
+    if (e->fit_in_flight && mjb_vf_fit_end(e, nullptr)) return -1;
     if (w) CK(e, cudaMemcpyAsync(e->vf_w, w, sizeof(float) * e->vf_d, cudaMemcpyDefault, e->stream));
     if (m) CK(e, cudaMemcpyAsync(e->vf_m, m, sizeof(float) * e->vf_d, cudaMemcpyDefault, e->stream));
     if (v) CK(e, cudaMemcpyAsync(e->vf_v, v, sizeof(float) * e->vf_d, cudaMemcpyDefault, e->stream));
@@ -880,6 +898,7 @@ int mjb_vf_set_state(mjb_engine* e, const float* w, const float* m, const float*
 }
 
 int mjb_vf_get_state(mjb_engine* e, float* w, float* m, float* v, int64_t* step) {
+    if (e->fit_in_flight && mjb_vf_fit_end(e, nullptr)) return -1;
     if (w && d2any(e, w, e->vf_w, sizeof(float) * e->vf_d)) return -1;
     if (m && d2any(e, m, e->vf_m, sizeof(float) * e->vf_d)) return -1;
     if (v && d2any(e, v, e->vf_v, sizeof(float) * e->vf_d)) return -1;
@@ -898,11 +917,14 @@ static int vf_error(mjb_engine* e, double* err) {
     return 0;
 }
 
-int mjb_vf_fit(mjb_engine* e, const int32_t* perms, int epochs, int batch_size, float lr, float reg_coef, double err_out[2]) {
+// Launch the whole fit (all epochs).  Communication, permutation upload and feature building run on the main
+// stream; the sequential Adam kernels run on `fs` (== main stream for the synchronous call, the side stream for
+// mjb_vf_fit_begin) behind an event, so the policy update can proceed concurrently on the remaining SMs.
+static int vf_fit_launch(mjb_engine* e, const int32_t* perms, int epochs, int batch_size, float lr, float reg_coef,
+                         cudaStream_t fs) {
     const long long N = e->n_glob_roll;
     const int steps = (int)(N / batch_size) - 1;            // optimize_model.py:24
     if (steps < 1) FAIL(e, "MLPBaseline.fit needs at least 2*batch_size samples (the reference crashes: optimize_model.py:24,35)");
-    if (err_out && vf_error(e, &err_out[0])) return -1;
     const float* fobs = e->obs; const int* ftstep = e->tstep; const double* fret = e->ret;
     if (e->comm) {
         // replicated sequential fit: gather every rank's (obs, tstep, returns) in rank order
@@ -932,41 +954,72 @@ int mjb_vf_fit(mjb_engine* e, const int32_t* perms, int epochs, int batch_size, 
         NK(e, g_nccl.GroupEnd());
         fobs = e->fit_obs; ftstep = e->fit_tstep; fret = e->fit_ret;
     }
-    if (N > e->perm_cap) {
+    if ((long long)epochs * N > e->perm_cap) {
         if (e->perm_dev) cudaFree(e->perm_dev);
-        e->perm_cap = N;
-        CK(e, cudaMalloc(&e->perm_dev, sizeof(int) * N));
+        e->perm_cap = (long long)epochs * N;
+        CK(e, cudaMalloc(&e->perm_dev, sizeof(int) * e->perm_cap));
     }
-    for (int ep = 0; ep < epochs; ++ep) {
-        CK(e, cudaMemcpyAsync(e->perm_dev, perms + (size_t)ep * N, sizeof(int) * N, cudaMemcpyDefault, e->stream));
-        if (e->comm) NK(e, g_nccl.Broadcast(e->perm_dev, e->perm_dev, N, ncclInt32, 0, e->comm, e->stream));
-        VfFitArgs a;
-        a.K = e->cfg.obs_dim + 4; a.H1 = e->cfg.vf_hidden[0]; a.H2 = e->cfg.vf_hidden[1]; a.obs_dim = e->cfg.obs_dim;
-        a.obs = fobs; a.tstep = ftstep; a.returns = fret; a.n = N; a.perm = e->perm_dev;
-        a.steps = steps; a.batch = batch_size; a.lr = lr; a.reg = reg_coef; a.beta1 = 0.9f; a.beta2 = 0.999f; a.eps = 1e-8f;
-        a.step0 = e->vf_step; a.w = e->vf_w; a.m = e->vf_m; a.v = e->vf_v; a.wT = e->vf_wT; a.loss_out = nullptr;
-        cudaError_t ce;
-        if (e->vf_cluster > 0 && e->vf_model_parallel && vf_mp_supported(a.K, a.H1, a.H2, a.batch, e->vf_cluster)) {
-            ce = launch_vf_fit_mp(a, e->vf_cluster, e->stream);
-            e->launches += 2;
-        } else if (e->vf_cluster > 0 && vf_cluster_supported(a.K, a.H1, a.H2, a.batch, e->vf_cluster)) {
-            if (!e->vf_cl_scratch)
-                CK(e, cudaMalloc(&e->vf_cl_scratch, sizeof(float) * vf_cluster_scratch_floats(a.K, a.H1, a.H2, 16)));
-            ce = launch_vf_fit_cluster(a, e->vf_cl_scratch, e->vf_cluster, e->stream);
-            e->launches += 2;
-        } else {
-            ce = launch_vf_fit(a, e->stream);
+    // all epochs' permutations go up front (the caller's host buffer is free again when this function returns)
+    CK(e, cudaMemcpyAsync(e->perm_dev, perms, sizeof(int) * (size_t)epochs * N, cudaMemcpyDefault, e->stream));
+    if (e->comm) NK(e, g_nccl.Broadcast(e->perm_dev, e->perm_dev, (size_t)epochs * N, ncclInt32, 0, e->comm, e->stream));
+    VfFitArgs a;
+    a.K = e->cfg.obs_dim + 4; a.H1 = e->cfg.vf_hidden[0]; a.H2 = e->cfg.vf_hidden[1]; a.obs_dim = e->cfg.obs_dim;
+    a.obs = fobs; a.tstep = ftstep; a.returns = fret; a.n = N;
+    a.steps = steps; a.batch = batch_size; a.lr = lr; a.reg = reg_coef; a.beta1 = 0.9f; a.beta2 = 0.999f; a.eps = 1e-8f;
+    a.w = e->vf_w; a.m = e->vf_m; a.v = e->vf_v; a.wT = e->vf_wT; a.loss_out = nullptr;
+    const bool use_mp = e->vf_cluster > 0 && e->vf_model_parallel && vf_mp_supported(a.K, a.H1, a.H2, a.batch, e->vf_cluster);
+    const bool use_dp = !use_mp && e->vf_cluster > 0 && vf_cluster_supported(a.K, a.H1, a.H2, a.batch, e->vf_cluster);
+    if (use_mp) {
+        if (N > e->vf_feat_cap) {
+            if (e->vf_feat) { cudaFree(e->vf_feat); cudaFree(e->vf_ret32); }
+            e->vf_feat_cap = N;
+            CK(e, cudaMalloc(&e->vf_feat, sizeof(float) * (size_t)N * a.K));
+            CK(e, cudaMalloc(&e->vf_ret32, sizeof(float) * (size_t)N));
         }
-        if (ce != cudaSuccess) FAIL(e, std::string("vf fit launch (batch<=64, multiple of 4; sizes must fit 220 KB smem): ") + cudaGetErrorString(ce));
+        if (vf_build_features(a, e->vf_feat, e->vf_ret32, e->stream) != cudaSuccess) FAIL(e, "vf feature kernel launch failed");
         e->launches += 1;
+    }
+    if (use_dp && !e->vf_cl_scratch)
+        CK(e, cudaMalloc(&e->vf_cl_scratch, sizeof(float) * vf_cluster_scratch_floats(a.K, a.H1, a.H2, 16)));
+    CK(e, cudaStreamSynchronize(e->stream));                 // host permutation buffer consumed; inputs of the fit complete
+    for (int ep = 0; ep < epochs; ++ep) {
+        a.perm = e->perm_dev + (size_t)ep * N;
+        a.step0 = e->vf_step;
+        cudaError_t ce;
+        if (use_mp) { ce = launch_vf_fit_mp(a, e->vf_feat, e->vf_ret32, e->vf_cluster, fs); e->launches += 2; }
+        else if (use_dp) { ce = launch_vf_fit_cluster(a, e->vf_cl_scratch, e->vf_cluster, fs); e->launches += 3; }
+        else { ce = launch_vf_fit(a, fs); e->launches += 1; }
+        if (ce != cudaSuccess) FAIL(e, std::string("vf fit launch (batch<=64, multiple of 4; sizes must fit 220 KB smem): ") + cudaGetErrorString(ce));
         e->vf_step += steps;
-        CK(e, cudaStreamSynchronize(e->stream));             // the host permutation buffer may be reused by the caller
+    }
+    return 0;
+}
+
+int mjb_vf_fit_end(mjb_engine* e, double* err_after) {
+    if (e->fit_in_flight) {
+        CK(e, cudaStreamSynchronize(e->stream_vf));
+        e->fit_in_flight = false;
     }
     launch_prep_mlp(e->vf_w, e->VPL, e->vf_prep, e->stream);
     e->launches += 1;
-    if (err_out && vf_error(e, &err_out[1])) return -1;
+    if (err_after && vf_error(e, err_after)) return -1;
     CK(e, cudaStreamSynchronize(e->stream));
     return 0;
+}
+
+int mjb_vf_fit_begin(mjb_engine* e, const int32_t* perms, int epochs, int batch_size, float lr, float reg_coef, double* err_before) {
+    if (e->fit_in_flight && mjb_vf_fit_end(e, nullptr)) return -1;
+    if (err_before && vf_error(e, err_before)) return -1;
+    if (vf_fit_launch(e, perms, epochs, batch_size, lr, reg_coef, e->stream_vf)) return -1;
+    e->fit_in_flight = true;
+    return 0;
+}
+
+int mjb_vf_fit(mjb_engine* e, const int32_t* perms, int epochs, int batch_size, float lr, float reg_coef, double err_out[2]) {
+    if (e->fit_in_flight && mjb_vf_fit_end(e, nullptr)) return -1;
+    if (err_out && vf_error(e, &err_out[0])) return -1;
+    if (vf_fit_launch(e, perms, epochs, batch_size, lr, reg_coef, e->stream)) return -1;
+    return mjb_vf_fit_end(e, err_out ? &err_out[1] : nullptr);
 }
 
 int mjb_event_record(mjb_engine* e, int slot) {
@@ -980,6 +1033,7 @@ int mjb_event_elapsed_ms(mjb_engine* e, int slot_a, int slot_b, float* ms) {
     CK(e, cudaEventElapsedTime(ms, e->user_ev[slot_a], e->user_ev[slot_b]));
     return 0;
 }
+
 // Developer aid (not part of the public header): per-phase clock64 cycle counters of the cluster fit kernel.
 int mjb_dev_vf_profile(mjb_engine* e, long long* out16, int enable) {
     static long long* dev = nullptr;

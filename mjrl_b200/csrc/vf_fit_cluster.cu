@@ -188,7 +188,6 @@ __global__ void __launch_bounds__(CT, 1) vf_fit_cluster_kernel(const ClArgs a) {
     for (int s = 0; s < a.steps; ++s) {
         if (tid == 0) {
             const float2 cc = cc_next;
-            if (s + 1 < a.steps) cc_next = a.consts[s + 1];   // consumed next step: off the critical path
             s_c.one_m_b1 = (float)(1.0 - (double)a.beta1);
             s_c.b2 = a.beta2;
             s_c.one_m_b2 = (float)(1.0 - (double)a.beta2);
@@ -197,8 +196,6 @@ __global__ void __launch_bounds__(CT, 1) vf_fit_cluster_kernel(const ClArgs a) {
             s_c.neg_step = cc.y;
             s_c.reg = a.reg;
         }
-        if (s + 1 < a.steps) load_vals();              // rows of step s+1: HBM-latency loads in flight during this step
-        if (s + 2 < a.steps) load_idx(s + 2);          // indices of step s+2
         // ---- forward layer 1: h1[n][q] = relu(sum_k x[k][q] W1T[k][n] + b1[n]) ----
         for (int o = tid; o < H1 * NQ; o += CT) {
             const int n = o % H1, q = o / H1;
@@ -369,7 +366,7 @@ __global__ void __launch_bounds__(CT, 1) vf_fit_cluster_kernel(const ClArgs a) {
             __stcg(gp + L.ob1 + tid, t);
         }
         MJB_PROF(5);
-        cluster.sync();                                   // #1: every CTA's partial is in L2
+        cluster_sync_relacq();                            // #1: every CTA's partial is in L2
         MJB_PROF(6);
         // ---- owner: sum the C partials of my slice, Adam, publish (all loads issued before any use) ----
         {
@@ -399,8 +396,13 @@ __global__ void __launch_bounds__(CT, 1) vf_fit_cluster_kernel(const ClArgs a) {
             }
         }
         MJB_PROF(7);
-        cluster.sync();                                   // #2: new weights visible
+        cluster_sync_relacq();                            // #2: new weights visible
         MJB_PROF(8);
+        // gather for the next step: issued after the last cluster barrier of this step (a barrier's release fence waits
+        // for every outstanding load of the thread), consumed by commit_prefetch() below
+        if (s + 1 < a.steps) load_vals();
+        if (s + 2 < a.steps) load_idx(s + 2);
+        if (tid == 0 && s + 1 < a.steps) cc_next = a.consts[s + 1];
         {   // reload all weights: one flat coalesced copy, loads batched ahead of the shared-memory stores
             constexpr int RB = 12;
             float4 r[RB];

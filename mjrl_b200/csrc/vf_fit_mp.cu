@@ -29,7 +29,9 @@ constexpr int NB = 64;         // minibatch rows
 
 struct MpArgs {
     int K, H1, H2, u1, u2, obs_dim, steps;
-    const float* obs; const int* tstep; const double* returns; const int* perm;
+    const float* feat;                       // [N][K] fp32 features (mlp_baseline.py:36-58), built once per fit
+    const float* ret32;                      // [N] float32(returns)
+    const int* perm;
     float lr, reg, beta1, beta2, eps;
     float* w; float* m; float* v;            // natural nn.Sequential layout, global
     const float2* consts;                    // per-step {sqrt(1-b2^t), -lr/(1-b1^t)}
@@ -101,10 +103,10 @@ __global__ void __launch_bounds__(MT_, 1) vf_fit_mp_kernel(const MpArgs a) {
     for (int i = tid; i < (K + H1 + 3 * u1 + u2) * BP + C * u1 * BP - u1 * BP + C * NB + MT_ * 4 + 2 * NB; i += MT_) xT[i] = 0.0f;
     __syncthreads();
 
-    // ---- minibatch gather pipeline: indices two steps ahead, raw rows one step ahead, in registers ----
+    // ---- minibatch gather pipeline: indices two steps ahead, feature rows one step ahead, in registers ----
     constexpr int NPF = 4;                         // NB*K <= NPF*MT_  (K <= 32)
     float pre_x[NPF];
-    double pre_t = 0.0;
+    float pre_t = 0.f;
     int r_nxt[NPF], rt_nxt = 0;
     auto load_idx = [&](int s) {
         const int* pidx = a.perm + (size_t)s * NB;
@@ -116,35 +118,17 @@ __global__ void __launch_bounds__(MT_, 1) vf_fit_mp_kernel(const MpArgs a) {
 #pragma unroll
         for (int u = 0; u < NPF; ++u) {
             const int e = tid + MT_ * u;
-            if (e < NB * K) {
-                const int k = e % K;
-                const long long r = r_nxt[u];
-                pre_x[u] = (k < a.obs_dim) ? a.obs[r * a.obs_dim + k] : __int_as_float(a.tstep[r]);
-            }
+            if (e < NB * K) pre_x[u] = a.feat[(size_t)r_nxt[u] * K + e % K];
         }
-        if (tid < NB) pre_t = a.returns[rt_nxt];
+        if (tid < NB) pre_t = a.ret32[rt_nxt];
     };
-    auto commit = [&]() {                          // feature map of mlp_baseline.py:36-58
+    auto commit = [&]() {
 #pragma unroll
         for (int u = 0; u < NPF; ++u) {
             const int e = tid + MT_ * u;
-            if (e < NB * K) {
-                const int k = e % K;
-                float val;
-                if (k < a.obs_dim) {
-                    double x = (double)pre_x[u];
-                    x = fmin(fmax(x, -10.0), 10.0) / 10.0;
-                    val = (float)x;
-                } else {
-                    const double tau = (double)__float_as_int(pre_x[u]) / 1000.0;
-                    double p = tau;
-                    for (int q = a.obs_dim; q < k; ++q) p *= tau;
-                    val = (float)p;
-                }
-                xT[k * BP + e / K] = val;
-            }
+            if (e < NB * K) xT[(e % K) * BP + e / K] = pre_x[u];
         }
-        if (tid < NB) tv[tid] = (float)pre_t;
+        if (tid < NB) tv[tid] = pre_t;
     };
     load_idx(0);
     load_vals();
@@ -152,19 +136,16 @@ __global__ void __launch_bounds__(MT_, 1) vf_fit_mp_kernel(const MpArgs a) {
     if (a.steps > 1) load_idx(1);
     float2 cc_next = make_float2(1.f, 0.f);
     if (tid == 0) cc_next = a.consts[0];
-    cluster.sync();                                // everybody's buffers are zeroed before any remote store
+    cluster_sync_relacq();                         // everybody's buffers are zeroed before any remote store
 
     long long t_last = clock64();
 #define MP_PROF(i) do { if (a.prof && tid == 0 && c == 0) { const long long _t = clock64(); a.prof[i] += _t - t_last; t_last = _t; } } while (0)
     for (int s = 0; s < a.steps; ++s) {
         if (tid == 0) {
             const float2 cc = cc_next;
-            if (s + 1 < a.steps) cc_next = a.consts[s + 1];
             s_c.one_m_b1 = (float)(1.0 - (double)a.beta1); s_c.b2 = a.beta2; s_c.one_m_b2 = (float)(1.0 - (double)a.beta2);
             s_c.bc2_sqrt = cc.x; s_c.eps = a.eps; s_c.neg_step = cc.y; s_c.reg = a.reg;
         }
-        if (s + 1 < a.steps) load_vals();
-        if (s + 2 < a.steps) load_idx(s + 2);
         // ---- P1: owned slice of layer 1 ----
         for (int o = tid; o < u1 * 16; o += MT_) {
             const int n = o % u1, q = o / u1;
@@ -190,7 +171,7 @@ __global__ void __launch_bounds__(MT_, 1) vf_fit_mp_kernel(const MpArgs a) {
             *reinterpret_cast<float4*>(dst + (c * u1 + n) * BP + 4 * q) = v;
         }
         MP_PROF(0);
-        cluster.sync();                            // #1: full h1 everywhere
+        cluster_sync_relacq();                     // #1: full h1 everywhere
         MP_PROF(1);
         // ---- P2: owned slice of layer 2 (reduction over H1 split in 4) ----
         {
@@ -230,7 +211,7 @@ __global__ void __launch_bounds__(MT_, 1) vf_fit_mp_kernel(const MpArgs a) {
             cluster.map_shared_rank(yp, r)[c * NB + b] = t;
         }
         MP_PROF(2);
-        cluster.sync();                            // #2: all partial outputs present
+        cluster_sync_relacq();                     // #2: all partial outputs present
         MP_PROF(3);
         if (tid < NB) {
             float y = 0.0f;
@@ -292,8 +273,14 @@ __global__ void __launch_bounds__(MT_, 1) vf_fit_mp_kernel(const MpArgs a) {
             }
         }
         MP_PROF(4);
-        cluster.sync();                            // #3: all partial dgrad slices delivered; W2 reads are done
+        cluster_sync_relacq();                     // #3: all partial dgrad slices delivered; W2 reads are done
         MP_PROF(5);
+        // Gather for the next step is issued HERE, after the last cluster barrier of this step: the barrier's release
+        // fence (MEMBAR.ALL.GPU in SASS) waits for every outstanding load of the thread, so loads issued earlier would
+        // put their HBM/L2 latency onto the barrier.  They complete under P4/P5 and are consumed by commit() below.
+        if (s + 1 < a.steps) load_vals();
+        if (s + 2 < a.steps) load_idx(s + 2);
+        if (tid == 0 && s + 1 < a.steps) cc_next = a.consts[s + 1];
         // ---- P4: delta1 of my units (fixed-order sum over the C sources), then W1 / b1 gradients ----
         for (int o = tid; o < u1 * 16; o += MT_) {
             const int n = o % u1, q = o / u1;
@@ -350,6 +337,30 @@ __global__ void __launch_bounds__(MT_, 1) vf_fit_mp_kernel(const MpArgs a) {
     }
 }
 
+// fp32 feature matrix of the whole batch, in the reference's dtypes: fp64 feature map, then .astype(float32)
+__global__ void vf_features_kernel(const float* __restrict__ obs, const int* __restrict__ tstep,
+                                   const double* __restrict__ returns, long long n, int obs_dim, int K,
+                                   float* __restrict__ feat, float* __restrict__ ret32) {
+    const long long total = n * K;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / K;
+        const int k = (int)(i - r * K);
+        float val;
+        if (k < obs_dim) {
+            double x = (double)obs[r * obs_dim + k];
+            x = fmin(fmax(x, -10.0), 10.0) / 10.0;
+            val = (float)x;
+        } else {
+            const double tau = (double)tstep[r] / 1000.0;
+            double p = tau;
+            for (int q = obs_dim; q < k; ++q) p *= tau;
+            val = (float)p;
+        }
+        feat[i] = val;
+        if (k == 0) ret32[r] = (float)returns[r];
+    }
+}
+
 __global__ void mp_adam_consts_kernel(float2* out, int steps, long long step0, float lr, float beta1, float beta2) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= steps) return;
@@ -401,7 +412,13 @@ bool vf_mp_supported(int K, int H1, int H2, int batch, int C) {
     return mp_smem_bytes(K, H1, H2, C) <= 200 * 1024;
 }
 
-cudaError_t launch_vf_fit_mp(const VfFitArgs& v, int C, cudaStream_t s) {
+// Build the fp32 feature matrix + fp32 targets once per fit (all epochs reuse them).
+cudaError_t vf_build_features(const VfFitArgs& v, float* feat, float* ret32, cudaStream_t s) {
+    vf_features_kernel<<<148 * 8, 256, 0, s>>>(v.obs, v.tstep, v.returns, v.n, v.obs_dim, v.K, feat, ret32);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_vf_fit_mp(const VfFitArgs& v, const float* feat, const float* ret32, int C, cudaStream_t s) {
     static float2* consts = nullptr;
     static int consts_cap = 0;
     if (v.steps > consts_cap) {
@@ -413,7 +430,7 @@ cudaError_t launch_vf_fit_mp(const VfFitArgs& v, int C, cudaStream_t s) {
     mp_adam_consts_kernel<<<(v.steps + 255) / 256, 256, 0, s>>>(consts, v.steps, v.step0, v.lr, v.beta1, v.beta2);
     MpArgs a;
     a.K = v.K; a.H1 = v.H1; a.H2 = v.H2; a.u1 = v.H1 / C; a.u2 = v.H2 / C; a.obs_dim = v.obs_dim; a.steps = v.steps;
-    a.obs = v.obs; a.tstep = v.tstep; a.returns = v.returns; a.perm = v.perm;
+    a.feat = feat; a.ret32 = ret32; a.perm = v.perm;
     a.lr = v.lr; a.reg = v.reg; a.beta1 = v.beta1; a.beta2 = v.beta2; a.eps = v.eps;
     a.w = v.w; a.m = v.m; a.v = v.v; a.consts = consts; a.prof = g_mp_prof;
     const size_t smem = mp_smem_bytes(v.K, v.H1, v.H2, C);

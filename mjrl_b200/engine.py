@@ -253,6 +253,20 @@ class Engine:
                                      C.byref(err) if return_errors else None), "vf_fit")
         return (err[0], err[1]) if return_errors else None
 
+    def vf_fit_begin(self, perms, batch_size=64, lr=1e-3, reg_coef=0.0, return_errors=False):
+        perms = np.ascontiguousarray(perms, dtype=np.int32)
+        if perms.ndim == 1:
+            perms = perms[None]
+        err = C.c_double()
+        self._ck(self.lib.mjb_vf_fit_begin(self.h, _ptr(perms), perms.shape[0], int(batch_size), float(lr), float(reg_coef),
+                                           C.byref(err) if return_errors else None), "vf_fit_begin")
+        return err.value if return_errors else None
+
+    def vf_fit_end(self, return_errors=False):
+        err = C.c_double()
+        self._ck(self.lib.mjb_vf_fit_end(self.h, C.byref(err) if return_errors else None), "vf_fit_end")
+        return err.value if return_errors else None
+
     def vf_set_cluster(self, ctas, model_parallel=True):
         self._ck(self.lib.mjb_vf_set_cluster(self.h, int(ctas), int(model_parallel)), "vf_set_cluster")
 
