@@ -139,6 +139,11 @@ int  mjb_policy_step(mjb_engine* e, int algo, double step_size_or_kl, double con
                      mjb_step_stats* out);
 int  mjb_policy_last_vectors(mjb_engine* e, float* vpg_out, float* npg_out);   /* g and x of the last step */
 
+/* FVP arithmetic: 1 (default where supported: 128x128 MLP, obs < 32, act <= 8) = tcgen05 tensor cores with two-term
+ * fp16 operand splitting (hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM); 0 = the fp32 FMA tile kernel.
+ * Returns 1 (not an error) when tensor cores were requested for a shape that only has the FMA kernel. */
+int  mjb_policy_set_tensor_cores(mjb_engine* e, int on);
+
 /* ---- MLP baseline (baselines/mlp_baseline.py, utils/optimize_model.py) ---------------------- */
 int  mjb_vf_dim(const mjb_engine* e);
 /* weights / Adam moments in nn.Sequential.parameters() order; step = optimizer step count. */

@@ -70,6 +70,7 @@ _SIGNATURES = {
     "mjb_policy_cg": (C.c_int, [_P, _P, C.c_int, C.c_float, C.c_float, _P, C.c_int64, _P]),
     "mjb_policy_step": (C.c_int, [_P, C.c_int, C.c_double, C.c_double, C.c_int, C.c_float, C.c_double, _P,
                                   C.c_int64, C.POINTER(StepStats)]),
+    "mjb_policy_set_tensor_cores": (C.c_int, [_P, C.c_int]),
     "mjb_policy_last_vectors": (C.c_int, [_P, _P, _P]),
     "mjb_vf_dim": (C.c_int, [_P]),
     "mjb_vf_set_state": (C.c_int, [_P, _P, _P, _P, C.c_int64]),

@@ -5,6 +5,7 @@
 #include <nccl.h>
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -75,6 +76,9 @@ struct mjb_engine {
     int d = 0, prep_total = 0, A = 0, tLS = 0;
     ParamSet pnew, pold;
     float* prep_tan = nullptr;
+    // tensor-core FVP path (fvp_tc.cu): fp16 hi/lo pre-tiled copies of theta_new and of the tangent
+    bool tc_ok = false, tc_on = true;
+    unsigned char* tc_prep_new = nullptr; unsigned char* tc_prep_tan = nullptr; float* tc_vscale = nullptr;
     bool old_equals_new = true, old_cache_valid = false, transforms_equal = true;
     long long cache_rows = 0;
     // ---- batch
@@ -132,6 +136,7 @@ enum {  // slots in dsc
     DS_CNT = 16,       // counts for all-reduce (4)
     DS_RET = 20,       // path-return stats: sum, sumsq, min, max, n
     DS_VF = 26,        // vf error sums (2)
+    DS_TCSCALE = 28,   // FVP scale with the tangent's power-of-two pre-scale undone (2)
     DS_TOTAL = 32
 };
 
@@ -183,6 +188,7 @@ int set_params(mjb_engine* e, ParamSet& ps, const float* theta_src) {
     if (e->linear) launch_prep_linear(ps.theta, e->LL, ps.prep, e->stream);
     else launch_prep_mlp(ps.theta, e->PL, ps.prep, e->stream);
     e->launches += 2;
+    if (e->tc_ok && &ps == &e->pnew) { launch_tc_prep(ps.theta, e->PL, nullptr, e->tc_prep_new, e->stream); e->launches += 1; }
     CK(e, cudaGetLastError());
     return 0;
 }
@@ -246,10 +252,32 @@ int ensure_old_cache(mjb_engine* e, long long rows) {
 
 // F v (undamped, all-reduced) into out.  v, out: device pointers of d floats.
 int fvp_device(mjb_engine* e, const float* v, const int* idx, long long n_idx, float* out) {
+    const long long n = idx ? n_idx : e->n_roll;
+    if (e->tc_ok && e->tc_on) {
+        // tensor-core path: scale v to O(1) (exact power of two), split to fp16 hi/lo, tcgen05 tile kernel
+        launch_tc_vscale(v, e->d, e->tc_vscale, e->stream);
+        launch_tc_prep(v, e->PL, e->tc_vscale, e->tc_prep_tan, e->stream);
+        const int sms = e->num_sms - (e->fit_in_flight ? std::max(e->vf_cluster, 1) : 0);
+        const long long tiles = (n + 127) / 128;
+        const int grid = (int)std::max<long long>(1, std::min<long long>(tiles, sms));
+        CK(e, cudaMemsetAsync(e->gpartial, 0, sizeof(float) * (size_t)grid * e->gstride, e->stream));
+        const int slot = (int)(e->fvp_count % mjb_engine::kFvpRing);
+        cudaEventRecord(e->fvp_ev[slot][0], e->stream);
+        cudaError_t ce = launch_fvp_tc(e->PL, e->tc_prep_new, e->tc_prep_tan, e->pnew.in_shift, e->pnew.in_scale,
+                                       e->pnew.out_scale, e->obs, idx, n, e->gpartial, e->gstride, grid, e->stream);
+        if (ce != cudaSuccess) FAIL(e, std::string("fvp_tc launch: ") + cudaGetErrorString(ce));
+        cudaEventRecord(e->fvp_ev[slot][1], e->stream);
+        e->fvp_count += 1;
+        double* sc = e->dsc + DS_TCSCALE;
+        launch_tc_scale_fix(e->dsc + (idx ? DS_SCALE_SUB : DS_SCALE), e->tc_vscale, sc, e->stream);
+        launch_reduce_partials(e->gpartial, grid, e->gstride, e->d, sc, out, e->pnew.theta, v, e->tLS, 1, e->stream);
+        e->launches += 5;
+        CK(e, cudaGetLastError());
+        return allreduce(e, out, e->d, ncclFloat);
+    }
     if (e->linear) launch_prep_linear(v, e->LL, e->prep_tan, e->stream);
     else launch_prep_mlp(v, e->PL, e->prep_tan, e->stream);
     e->launches += 1;
-    const long long n = idx ? n_idx : e->n_roll;
     const int slot = (int)(e->fvp_count % mjb_engine::kFvpRing);
     // the memset of the gradient partials belongs to the FVP; the event pair brackets memset + tile kernel
     cudaEventRecord(e->fvp_ev[slot][0], e->stream);
@@ -369,7 +397,7 @@ void mjb_destroy(mjb_engine* e) {
     if (e->comm) g_nccl.CommDestroy(e->comm);
     void* bufs[] = {e->pnew.theta, e->pnew.prep, e->pnew.in_shift, e->pnew.in_scale, e->pnew.out_shift, e->pnew.out_scale,
                     e->pold.theta, e->pold.prep, e->pold.in_shift, e->pold.in_scale, e->pold.out_shift, e->pold.out_scale,
-                    e->prep_tan, e->obs, e->act, e->rew, e->path_off, e->term, e->tstep, e->ret, e->adv, e->base,
+                    e->prep_tan, e->tc_prep_new, e->tc_prep_tan, e->tc_vscale, e->obs, e->act, e->rew, e->path_off, e->term, e->tstep, e->ret, e->adv, e->base,
                     e->adv_white, e->weights, e->path_ret, e->ll_old, e->mu_old, e->gpartial, e->eval_partial,
                     e->mom_scratch, e->dsc, e->g, e->x, e->r, e->p, e->Fp, e->tmpv, e->idx_dev, e->stage64, e->vf_w,
                     e->vf_m, e->vf_v, e->vf_wT, e->vf_prep, e->vf_cl_scratch, e->vf_feat, e->vf_ret32, e->perm_dev, e->fit_obs, e->fit_tstep, e->fit_ret};
@@ -442,6 +470,11 @@ int mjb_create(const mjb_config* cfg, mjb_engine** out) {
         cudaStreamSynchronize(e->stream);
     }
     ALLOC(e->prep_tan, e->prep_total);
+    e->tc_ok = !e->linear && fvp_tc_supported(e->PL);
+    if (const char* env = getenv("MJRL_B200_TC")) e->tc_on = atoi(env) != 0;
+    if (e->tc_ok) {
+        ALLOC(e->tc_prep_new, fvp_tc_prep_bytes()); ALLOC(e->tc_prep_tan, fvp_tc_prep_bytes()); ALLOC(e->tc_vscale, 2);
+    }
     ALLOC(e->obs, N * O); ALLOC(e->act, N * A); ALLOC(e->rew, N);
     ALLOC(e->path_off, (size_t)cfg->max_paths + 2); ALLOC(e->term, (size_t)cfg->max_paths + 1); ALLOC(e->tstep, N);
     ALLOC(e->ret, N); ALLOC(e->adv, N); ALLOC(e->base, N); ALLOC(e->adv_white, N); ALLOC(e->weights, N);
@@ -1043,6 +1076,11 @@ int mjb_dev_vf_profile(mjb_engine* e, long long* out16, int enable) {
     CK(e, cudaMemcpy(out16, dev, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
     vf_cluster_set_prof(nullptr); vf_mp_set_prof(nullptr);
     return 0;
+}
+
+int mjb_policy_set_tensor_cores(mjb_engine* e, int on) {
+    e->tc_on = on != 0;
+    return (e->tc_ok || !on) ? 0 : 1;       // 1: requested but this shape runs on the fp32 FMA kernels
 }
 
 int mjb_vf_set_cluster(mjb_engine* e, int cluster_ctas, int model_parallel) {

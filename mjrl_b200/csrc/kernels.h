@@ -83,6 +83,16 @@ void launch_axpy_clamp(const float* theta, const float* x, const double* alpha_d
                        int d, int A, float lo, float* out, cudaStream_t s);
 void launch_scale(float* x, int d, float s_, cudaStream_t s);
 
+// ---- fvp_tc.cu : tcgen05 / TMEM Fisher-vector product for the 128x128 MLP
+size_t fvp_tc_prep_bytes();
+bool fvp_tc_supported(const PrepLayout& L);
+void launch_tc_prep(const float* theta, const PrepLayout& L, const float* scale_dev, unsigned char* out, cudaStream_t s);
+void launch_tc_vscale(const float* v, int d, float* out2, cudaStream_t s);
+void launch_tc_scale_fix(const double* in2, const float* vscale2, double* out2, cudaStream_t s);
+cudaError_t launch_fvp_tc(const PrepLayout& L, const unsigned char* P, const unsigned char* T, const float* in_shift,
+                          const float* in_scale, const float* out_scale, const float* obs, const int* idx, long long n,
+                          float* gpartial, long long gstride, int grid, cudaStream_t s);
+
 // ---- vf_fit.cu : sequential minibatch Adam of the value net
 struct VfFitArgs {
     int K, H1, H2, obs_dim;           // K = obs_dim + 4

@@ -227,6 +227,10 @@ class Engine:
                                           0 if ii is None else ii.shape[1], C.byref(st)), "policy_step")
         return st
 
+    def set_tensor_cores(self, on=True):
+        """Returns True when the tcgen05 FVP path is active for this policy shape."""
+        return self.lib.mjb_policy_set_tensor_cores(self.h, int(on)) == 0 and bool(on)
+
     def last_vectors(self):
         g = np.empty(self.d, dtype=np.float32)
         x = np.empty(self.d, dtype=np.float32)

@@ -251,3 +251,42 @@ def test_shapes_vs_oracle(shape, cuda_device):
     assert abs(kl / float(O.mean_kl(spec, th2, th, obs)) - 1) < 1e-3
     assert rel(eng.vpg(), O.flat_vpg(spec, th2, obs, act, white, theta_old=th)) < 2e-5
     eng.close()
+
+
+def test_tensor_core_fvp_matches_fma_and_oracle(cuda_device):
+    """The tcgen05 FVP (two-term fp16 split, fp32 accumulation in TMEM) against the fp32-FMA kernel, the fp64 oracle
+    and the reference fixture, including a ragged tail tile, a subsample gather and a badly scaled tangent."""
+    g = load_golden("cheetah_24x500")
+    paths = golden_paths(g)
+    m = g["meta"]
+    eng = make_engine(g, cuda_device)
+    eng.upload_paths(paths)
+    obs = np.concatenate([p["observations"] for p in paths])
+    spec = O.PolicySpec(m["obs_dim"], m["act_dim"], m["hidden"])
+    assert eng.set_tensor_cores(True) is True
+    rng = np.random.RandomState(5)
+    for scale in (1.0, 1e-6, 3e4):
+        v = (scale * rng.randn(spec.d)).astype(np.float32)
+        want = O.fvp(spec, g["theta0"], obs, v, m["damping"])
+        eng.set_tensor_cores(True)
+        tc = eng.fvp(v, m["damping"])
+        eng.set_tensor_cores(False)
+        fma = eng.fvp(v, m["damping"])
+        assert rel(fma, want) < 1e-5
+        assert rel(tc, want) < 1e-5, rel(tc, want)
+    eng.set_tensor_cores(True)
+    assert rel(eng.fvp(g["fvp_vec"], m["damping"]), g["fvp_out"]) < 1e-5
+    idx = rng.randint(0, eng.n, size=eng.n // 3).astype(np.int32)
+    v = rng.randn(spec.d).astype(np.float32)
+    assert rel(eng.fvp(v, m["damping"], idx=idx), O.fvp(spec, g["theta0"], obs[idx], v, m["damping"])) < 1e-5
+    # non-default log_std / transforms flow through the tensor-core path too
+    th = g["theta0"].copy()
+    th[-m["act_dim"]:] = 0.3 * rng.randn(m["act_dim"])
+    eng.set_params(th)
+    assert rel(eng.fvp(v, 1e-4), O.fvp(spec, th, obs, v, 1e-4)) < 1e-5
+    # shapes without a tensor-core kernel report it and keep working on the FMA kernels
+    g2 = load_golden("swim_40x250")
+    e2 = make_engine(g2, cuda_device)
+    assert e2.set_tensor_cores(True) is False
+    e2.close()
+    eng.close()
