@@ -48,50 +48,89 @@ __device__ __forceinline__ float adam_apply(float g, float w, float* m, float* v
     return fmaf(c.neg_step, mn / (sqrtf(vn) / c.bc2_sqrt + c.eps), w);
 }
 
-template <int C>
+// remote (distributed shared memory) helpers: addresses are 32-bit shared::cluster addresses
+__device__ __forceinline__ uint32_t map_cluster(const void* local_smem, int cta) {
+    uint32_t l = (uint32_t)__cvta_generic_to_shared(local_smem), r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(l), "r"(cta));
+    return r;
+}
+// asynchronous 16-byte store into another CTA's shared memory; completion is counted (16 bytes) on that CTA's mbarrier
+__device__ __forceinline__ void st_async_v4(uint32_t raddr, float4 v, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];\n"
+                 ::"r"(raddr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)),
+                   "r"(__float_as_uint(v.w)), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void st_async_f32(uint32_t raddr, float v, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];\n"
+                 ::"r"(raddr), "r"(__float_as_uint(v)), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arm(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra D_%=;\n\tbra W_%=;\n\t"
+        "D_%=:\n\t}\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
+// C CTAs, hidden width H (both layers), u = H/C owned units per CTA.  K (input features) is a run-time value.
+template <int C, int H>
 __global__ void __launch_bounds__(MT_, 1) vf_fit_mp_kernel(const MpArgs a) {
-    cg::cluster_group cluster = cg::this_cluster();
-    const int c = (int)cluster.block_rank();
-    const int K = a.K, H1 = a.H1, H2 = a.H2, u1 = a.u1, u2 = a.u2;
-    const int W2P = H1 + 4;                       // pitch of owned W2 rows
+    constexpr int U = H / C;                      // owned units per layer
+    constexpr int W2P = H + 4;                    // pitch of owned W2 rows
+    constexpr int ITEMS = U * 16;                 // (unit, row-quad) work items of an owned slice
+    constexpr int KS = MT_ / ITEMS;               // reduction split of the layer-2 slice
+    constexpr int KR = H / KS;
+    constexpr int NG = MT_ / H;                   // thread groups along the owned rows in the W2 weight gradient
+    constexpr int PER = (U + NG - 1) / NG;
+    static_assert(ITEMS * KS == MT_ && KR * KS == H && PER <= 4 && NG * H == MT_, "shape not covered");
+    uint32_t c;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(c));
+    const int K = a.K;
     const int tid = threadIdx.x;
     extern __shared__ __align__(16) float sm[];
     // ---- owned parameters + Adam state (persist for the whole epoch) ----
-    float* W1o = sm;                              // [u1][K]
-    float* b1o = W1o + u1 * K;                    // [u1]
-    float* W2o = b1o + u1;                        // [u2][W2P]
-    float* b2o = W2o + u2 * W2P;                  // [u2]
-    float* W3o = b2o + u2;                        // [u2]
-    float* b3r = W3o + u2;                        // [1] replicated in every CTA (identical updates)
-    const int np = u1 * K + u1 + u2 * W2P + 2 * u2 + 1;
+    float* W1o = sm;                              // [U][K]
+    float* b1o = W1o + U * K;                     // [U]
+    float* W2o = b1o + U;                         // [U][W2P]
+    float* b2o = W2o + U * W2P;                   // [U]
+    float* W3o = b2o + U;                         // [U]
+    float* b3r = W3o + U;                         // [1] replicated in every CTA (identical updates)
+    const int np = U * K + U + U * W2P + 2 * U + 1;
     const int npp = round_up(np, 4);
     float* Mo = sm + npp;                         // Adam exp_avg, same indexing as the parameter block
     float* Vo = Mo + npp;                         // Adam exp_avg_sq
-    // ---- per-step buffers ----
-    float* xT = Vo + npp;                         // [K][BP]      minibatch features (all 64 rows)
-    float* h1f = xT + K * BP;                     // [H1][BP]     full h1, assembled from every CTA's slice
-    float* h1o = h1f + H1 * BP;                   // [u1][BP]     owned slice of h1
-    float* h2o = h1o + u1 * BP;                   // [u2][BP]     owned slice of h2, then delta2
-    float* d1o = h2o + u2 * BP;                   // [u1][BP]     owned slice of delta1
-    float* dg = d1o + u1 * BP;                    // [C][u1][BP]  partial dgrad slices received from every CTA
-    float* yp = dg + C * u1 * BP;                 // [C][NB]      partial outputs received from every CTA
-    float* red = yp + C * NB;                     // [MT_][4]     k-split partials
+    // ---- per-step buffers; the three exchange buffers are double-buffered by step parity ----
+    float* xT = Vo + npp;                         // [K][BP]        minibatch features (all 64 rows)
+    float* h1o = xT + K * BP;                     // [U][BP]        owned slice of h1
+    float* h2o = h1o + U * BP;                    // [U][BP]        owned slice of h2, then delta2
+    float* d1o = h2o + U * BP;                    // [U][BP]        owned slice of delta1
+    float* red = d1o + U * BP;                    // [MT_][4]       k-split partials
     float* tv = red + MT_ * 4;                    // [NB] targets
     float* dy = tv + NB;                          // [NB]
+    float* h1f = dy + NB;                         // [2][H][BP]     full h1 (every CTA's slice lands here)
+    float* dg = h1f + 2 * H * BP;                 // [2][C][U][BP]  partial dgrad slices from every CTA
+    float* yp = dg + 2 * C * U * BP;              // [2][C][NB]     partial outputs from every CTA
     __shared__ AdamP s_c;
+    __shared__ __align__(8) uint64_t bars[3][2];  // [exchange][step parity]
 
-    // ---- load owned parameters / moments from the natural layout ----
-    const int oW1 = 0, ob1 = H1 * K, oW2 = ob1 + H1, ob2 = oW2 + H2 * H1, oW3 = ob2 + H2, ob3 = oW3 + H2;
+    const int oW1 = 0, ob1 = H * K, oW2 = ob1 + H, ob2 = oW2 + H * H, oW3 = ob2 + H, ob3 = oW3 + H;
     auto nat_index = [&](int p) -> int {          // owned-block index -> natural flat index
-        if (p < u1 * K) return oW1 + (c * u1 + p / K) * K + p % K;
-        p -= u1 * K;
-        if (p < u1) return ob1 + c * u1 + p;
-        p -= u1;
-        if (p < u2 * W2P) { const int n = p / W2P, k = p % W2P; return k < H1 ? oW2 + (c * u2 + n) * H1 + k : -1; }
-        p -= u2 * W2P;
-        if (p < u2) return ob2 + c * u2 + p;
-        p -= u2;
-        if (p < u2) return oW3 + c * u2 + p;
+        if (p < U * K) return oW1 + ((int)c * U + p / K) * K + p % K;
+        p -= U * K;
+        if (p < U) return ob1 + (int)c * U + p;
+        p -= U;
+        if (p < U * W2P) { const int n = p / W2P, k = p % W2P; return k < H ? oW2 + ((int)c * U + n) * H + k : -1; }
+        p -= U * W2P;
+        if (p < U) return ob2 + (int)c * U + p;
+        p -= U;
+        if (p < U) return oW3 + (int)c * U + p;
         return ob3;
     };
     for (int p = tid; p < np; p += MT_) {
@@ -100,7 +139,10 @@ __global__ void __launch_bounds__(MT_, 1) vf_fit_mp_kernel(const MpArgs a) {
         Mo[p] = j >= 0 ? a.m[j] : 0.0f;
         Vo[p] = j >= 0 ? a.v[j] : 0.0f;
     }
-    for (int i = tid; i < (K + H1 + 3 * u1 + u2) * BP + C * u1 * BP - u1 * BP + C * NB + MT_ * 4 + 2 * NB; i += MT_) xT[i] = 0.0f;
+    const int nbuf = (K + 3 * U) * BP + MT_ * 4 + 2 * NB + 2 * H * BP + 2 * C * U * BP + 2 * C * NB;
+    for (int i = tid; i < nbuf; i += MT_) xT[i] = 0.0f;
+    if (tid < 6) bar_init(&bars[tid >> 1][tid & 1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     __syncthreads();
 
     // ---- minibatch gather pipeline: indices two steps ahead, feature rows one step ahead, in registers ----
@@ -136,19 +178,28 @@ __global__ void __launch_bounds__(MT_, 1) vf_fit_mp_kernel(const MpArgs a) {
     if (a.steps > 1) load_idx(1);
     float2 cc_next = make_float2(1.f, 0.f);
     if (tid == 0) cc_next = a.consts[0];
-    cluster_sync_relacq();                         // everybody's buffers are zeroed before any remote store
+    cluster_sync_relacq();                         // barriers initialised and buffers zeroed everywhere before any remote store
 
     long long t_last = clock64();
 #define MP_PROF(i) do { if (a.prof && tid == 0 && c == 0) { const long long _t = clock64(); a.prof[i] += _t - t_last; t_last = _t; } } while (0)
     for (int s = 0; s < a.steps; ++s) {
+        const int par = s & 1;
+        const uint32_t ph = (uint32_t)(s >> 1) & 1u;          // phase parity of the barriers of this step parity
+        float* h1f_s = h1f + par * H * BP;
+        float* dg_s = dg + par * C * U * BP;
+        float* yp_s = yp + par * C * NB;
         if (tid == 0) {
             const float2 cc = cc_next;
             s_c.one_m_b1 = (float)(1.0 - (double)a.beta1); s_c.b2 = a.beta2; s_c.one_m_b2 = (float)(1.0 - (double)a.beta2);
             s_c.bc2_sqrt = cc.x; s_c.eps = a.eps; s_c.neg_step = cc.y; s_c.reg = a.reg;
+            // arm this step's three hand-off barriers with the bytes every CTA (incl. myself) will deliver
+            bar_arm(&bars[0][par], C * U * NB * 4);
+            bar_arm(&bars[1][par], C * NB * 4);
+            bar_arm(&bars[2][par], C * U * NB * 4);
         }
         // ---- P1: owned slice of layer 1 ----
-        for (int o = tid; o < u1 * 16; o += MT_) {
-            const int n = o % u1, q = o / u1;
+        if (tid < ITEMS) {
+            const int n = tid % U, q = tid / U;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             const float* wr = W1o + n * K;
 #pragma unroll 4
@@ -162,39 +213,37 @@ __global__ void __launch_bounds__(MT_, 1) vf_fit_mp_kernel(const MpArgs a) {
             *reinterpret_cast<float4*>(h1o + n * BP + 4 * q) = acc;
         }
         __syncthreads();
-        // ---- E1: my h1 slice -> every CTA's full h1 ----
-        for (int i = tid; i < u1 * 16 * C; i += MT_) {
-            const int item = i % (u1 * 16), r = i / (u1 * 16);
-            const int n = item % u1, q = item / u1;
+        // ---- E1: my h1 slice -> every CTA's full h1 (asynchronous remote stores, counted on the receiver's barrier) ----
+#pragma unroll
+        for (int i = tid; i < ITEMS * C; i += MT_) {
+            const int item = i % ITEMS, r = i / ITEMS;
+            const int n = item % U, q = item / U;
             const float4 v = *reinterpret_cast<const float4*>(h1o + n * BP + 4 * q);
-            float* dst = cluster.map_shared_rank(h1f, r);
-            *reinterpret_cast<float4*>(dst + (c * u1 + n) * BP + 4 * q) = v;
+            st_async_v4(map_cluster(h1f_s + ((int)c * U + n) * BP + 4 * q, r), v, map_cluster(&bars[0][par], r));
         }
         MP_PROF(0);
-        cluster_sync_relacq();                     // #1: full h1 everywhere
+        bar_wait_cluster(&bars[0][par], ph);       // full h1 has arrived
         MP_PROF(1);
-        // ---- P2: owned slice of layer 2 (reduction over H1 split in 4) ----
+        // ---- P2: owned slice of layer 2 (reduction over H split KS ways) ----
         {
-            const int items = u2 * 16, KS = MT_ / items, kr = H1 / KS;       // items*KS == MT_ for u2*16 | 512
-            const int item = tid % items, ks = tid / items;
-            const int n = item % u2, q = item / u2;
+            const int item = tid % ITEMS, ks = tid / ITEMS;
+            const int n = item % U, q = item / U;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ks < KS) {
-                const float* wr = W2o + n * W2P + ks * kr;
-                const float* hp = h1f + (ks * kr) * BP + 4 * q;
+            const float* wr = W2o + n * W2P + ks * KR;
+            const float* hp = h1f_s + (ks * KR) * BP + 4 * q;
 #pragma unroll 8
-                for (int i = 0; i < kr; ++i) {
-                    const float w = wr[i];
-                    const float4 x = *reinterpret_cast<const float4*>(hp + i * BP);
-                    acc.x = fmaf(x.x, w, acc.x); acc.y = fmaf(x.y, w, acc.y); acc.z = fmaf(x.z, w, acc.z); acc.w = fmaf(x.w, w, acc.w);
-                }
+            for (int i = 0; i < KR; ++i) {
+                const float w = wr[i];
+                const float4 x = *reinterpret_cast<const float4*>(hp + i * BP);
+                acc.x = fmaf(x.x, w, acc.x); acc.y = fmaf(x.y, w, acc.y); acc.z = fmaf(x.z, w, acc.z); acc.w = fmaf(x.w, w, acc.w);
             }
             *reinterpret_cast<float4*>(red + tid * 4) = acc;
             __syncthreads();
-            if (tid < items) {
+            if (tid < ITEMS) {
                 float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
                 for (int k2 = 0; k2 < KS; ++k2) {
-                    const float4 r = *reinterpret_cast<const float4*>(red + (k2 * items + tid) * 4);
+                    const float4 r = *reinterpret_cast<const float4*>(red + (k2 * ITEMS + tid) * 4);
                     t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
                 }
                 const float bb = b2o[n];
@@ -207,26 +256,28 @@ __global__ void __launch_bounds__(MT_, 1) vf_fit_mp_kernel(const MpArgs a) {
         for (int i = tid; i < NB * C; i += MT_) {
             const int b = i % NB, r = i / NB;
             float t = 0.0f;
-            for (int n = 0; n < u2; ++n) t = fmaf(h2o[n * BP + b], W3o[n], t);
-            cluster.map_shared_rank(yp, r)[c * NB + b] = t;
+#pragma unroll
+            for (int n = 0; n < U; ++n) t = fmaf(h2o[n * BP + b], W3o[n], t);
+            st_async_f32(map_cluster(yp_s + (int)c * NB + b, r), t, map_cluster(&bars[1][par], r));
         }
         MP_PROF(2);
-        cluster_sync_relacq();                     // #2: all partial outputs present
+        bar_wait_cluster(&bars[1][par], ph);
         MP_PROF(3);
         if (tid < NB) {
             float y = 0.0f;
-            for (int r = 0; r < C; ++r) y += yp[r * NB + tid];
+#pragma unroll
+            for (int r = 0; r < C; ++r) y += yp_s[r * NB + tid];
             dy[tid] = 2.0f * ((y + b3r[0]) - tv[tid]) / (float)NB;
         }
         __syncthreads();
         const AdamP ck = s_c;
-        // ---- P3: delta2 (in place of h2), small gradients ----
-        float g_small = 0.0f;                      // thread n<u2: gW3[n]; thread u2+n: gb2[n] (after delta2); thread 2*u2: gb3
-        if (tid < u2) { for (int b = 0; b < NB; ++b) g_small = fmaf(dy[b], h2o[tid * BP + b], g_small); }
-        else if (tid == 2 * u2) { for (int b = 0; b < NB; ++b) g_small += dy[b]; }
+        // ---- P3: small gradients, delta2 (in place of h2) ----
+        float g_small = 0.0f;                      // thread n<U: gW3[n]; thread U+n: gb2[n] (after delta2); thread 2U: gb3
+        if (tid < U) { for (int b = 0; b < NB; ++b) g_small = fmaf(dy[b], h2o[tid * BP + b], g_small); }
+        else if (tid == 2 * U) { for (int b = 0; b < NB; ++b) g_small += dy[b]; }
         __syncthreads();
-        for (int o = tid; o < u2 * 16; o += MT_) {
-            const int n = o % u2, q = o / u2;
+        if (tid < ITEMS) {
+            const int n = tid % U, q = tid / U;
             const float w3 = W3o[n];
             float4 h = *reinterpret_cast<const float4*>(h2o + n * BP + 4 * q);
             const float4 d = *reinterpret_cast<const float4*>(dy + 4 * q);
@@ -235,14 +286,16 @@ __global__ void __launch_bounds__(MT_, 1) vf_fit_mp_kernel(const MpArgs a) {
             *reinterpret_cast<float4*>(h2o + n * BP + 4 * q) = h;
         }
         __syncthreads();
-        if (tid >= u2 && tid < 2 * u2) { for (int b = 0; b < NB; ++b) g_small += h2o[(tid - u2) * BP + b]; }
+        if (tid >= U && tid < 2 * U) { for (int b = 0; b < NB; ++b) g_small += h2o[(tid - U) * BP + b]; }
         // ---- partial dgrad over my units, scattered to the owners of each h1 unit (E3) ----
-        for (int o = tid; o < H1 * 4; o += MT_) {
-            const int k = o % H1, qg = o / H1;                 // 4 quads per thread
+#pragma unroll
+        for (int o = tid; o < H * 4; o += MT_) {
+            const int k = o % H, qg = o / H;                   // 4 row-quads per thread
             float4 acc[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int n = 0; n < u2; ++n) {
+#pragma unroll
+            for (int n = 0; n < U; ++n) {
                 const float w = W2o[n * W2P + k];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -251,20 +304,22 @@ __global__ void __launch_bounds__(MT_, 1) vf_fit_mp_kernel(const MpArgs a) {
                     acc[j].z = fmaf(d.z, w, acc[j].z); acc[j].w = fmaf(d.w, w, acc[j].w);
                 }
             }
-            float* dst = cluster.map_shared_rank(dg, k / u1) + (c * u1 + k % u1) * BP;
+            const int r = k / U;
+            const uint32_t dst = map_cluster(dg_s + ((int)c * U + k % U) * BP, r), rb = map_cluster(&bars[2][par], r);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(dst + 4 * (4 * qg + j)) = acc[j];
+            for (int j = 0; j < 4; ++j) st_async_v4(dst + 4 * (4 * (4 * qg + j)), acc[j], rb);
         }
         // ---- wgrad of my W2 rows: g[n][k] = sum_b delta2[n][b] h1[k][b]  (kept in registers until the update) ----
         float gw2[4] = {0.f, 0.f, 0.f, 0.f};
         {
-            const int k = tid % H1, ng = tid / H1, NG = MT_ / H1, per = (u2 + NG - 1) / NG;   // per <= 4
+            const int k = tid % H, ng = tid / H;
+#pragma unroll 4
             for (int q = 0; q < 16; ++q) {
-                const float4 h = *reinterpret_cast<const float4*>(h1f + k * BP + 4 * q);
+                const float4 h = *reinterpret_cast<const float4*>(h1f_s + k * BP + 4 * q);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int n = ng * per + j;
-                    if (j < per && n < u2) {
+                for (int j = 0; j < PER; ++j) {
+                    const int n = ng * PER + j;
+                    if (n < U) {
                         const float4 d = *reinterpret_cast<const float4*>(h2o + n * BP + 4 * q);
                         gw2[j] = fmaf(d.x, h.x, gw2[j]); gw2[j] = fmaf(d.y, h.y, gw2[j]);
                         gw2[j] = fmaf(d.z, h.z, gw2[j]); gw2[j] = fmaf(d.w, h.w, gw2[j]);
@@ -272,60 +327,62 @@ __global__ void __launch_bounds__(MT_, 1) vf_fit_mp_kernel(const MpArgs a) {
                 }
             }
         }
-        MP_PROF(4);
-        cluster_sync_relacq();                     // #3: all partial dgrad slices delivered; W2 reads are done
-        MP_PROF(5);
-        // Gather for the next step is issued HERE, after the last cluster barrier of this step: the barrier's release
-        // fence (MEMBAR.ALL.GPU in SASS) waits for every outstanding load of the thread, so loads issued earlier would
-        // put their HBM/L2 latency onto the barrier.  They complete under P4/P5 and are consumed by commit() below.
+        // Gather for the next step is issued here: nothing below waits on a fence that would stall on these loads.
         if (s + 1 < a.steps) load_vals();
         if (s + 2 < a.steps) load_idx(s + 2);
         if (tid == 0 && s + 1 < a.steps) cc_next = a.consts[s + 1];
-        // ---- P4: delta1 of my units (fixed-order sum over the C sources), then W1 / b1 gradients ----
-        for (int o = tid; o < u1 * 16; o += MT_) {
-            const int n = o % u1, q = o / u1;
+        MP_PROF(4);
+        bar_wait_cluster(&bars[2][par], ph);       // every partial dgrad slice destined to me has arrived
+        MP_PROF(5);
+        // ---- P4: delta1 of my units (fixed-order sum over the C sources) ----
+        if (tid < ITEMS) {
+            const int n = tid % U, q = tid / U;
             float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
             for (int r = 0; r < C; ++r) {
-                const float4 d = *reinterpret_cast<const float4*>(dg + (r * u1 + n) * BP + 4 * q);
+                const float4 d = *reinterpret_cast<const float4*>(dg_s + (r * U + n) * BP + 4 * q);
                 t.x += d.x; t.y += d.y; t.z += d.z; t.w += d.w;
             }
             const float4 h = *reinterpret_cast<const float4*>(h1o + n * BP + 4 * q);
             t.x = h.x > 0.f ? t.x : 0.f; t.y = h.y > 0.f ? t.y : 0.f; t.z = h.z > 0.f ? t.z : 0.f; t.w = h.w > 0.f ? t.w : 0.f;
             *reinterpret_cast<float4*>(d1o + n * BP + 4 * q) = t;
         }
-        __syncthreads();
+        __syncthreads();                           // also: every thread is past its reads of W2o (dgrad) -> safe to update
         // ---- P5: Adam on everything I own ----
-        {   // W2 rows
-            const int k = tid % H1, ng = tid / H1, NG = MT_ / H1, per = (u2 + NG - 1) / NG;
+        {
+            const int k = tid % H, ng = tid / H;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int n = ng * per + j;
-                if (j < per && n < u2) {
+            for (int j = 0; j < PER; ++j) {
+                const int n = ng * PER + j;
+                if (n < U) {
                     float* p = W2o + n * W2P + k;
                     *p = adam_apply(gw2[j], *p, Mo + (p - sm), Vo + (p - sm), ck);
                 }
             }
         }
-        for (int o = tid; o < u1 * K; o += MT_) {   // W1 rows
-            const int n = o / K, k = o - n * K;
+        for (int o = tid; o < U * K; o += MT_) {    // W1 rows
+            const int n = o % U, k = o / U;
             float g = 0.0f;
+#pragma unroll 4
             for (int q = 0; q < 16; ++q) {
                 const float4 d = *reinterpret_cast<const float4*>(d1o + n * BP + 4 * q);
                 const float4 x = *reinterpret_cast<const float4*>(xT + k * BP + 4 * q);
                 g = fmaf(d.x, x.x, g); g = fmaf(d.y, x.y, g); g = fmaf(d.z, x.z, g); g = fmaf(d.w, x.w, g);
             }
-            W1o[o] = adam_apply(g, W1o[o], Mo + o, Vo + o, ck);
-        }
-        if (tid < u1) {                            // b1
-            float g = 0.0f;
-            for (int b = 0; b < NB; ++b) g += d1o[tid * BP + b];
-            float* p = b1o + tid;
+            float* p = W1o + n * K + k;
             *p = adam_apply(g, *p, Mo + (p - sm), Vo + (p - sm), ck);
         }
-        __syncthreads();                           // W3 / b2 / b3 are read above by other threads this step: update last
-        if (tid < u2) { float* p = W3o + tid; *p = adam_apply(g_small, *p, Mo + (p - sm), Vo + (p - sm), ck); }
-        else if (tid < 2 * u2) { float* p = b2o + (tid - u2); *p = adam_apply(g_small, *p, Mo + (p - sm), Vo + (p - sm), ck); }
-        else if (tid == 2 * u2) { float* p = b3r; *p = adam_apply(g_small, *p, Mo + (p - sm), Vo + (p - sm), ck); }
+        if (tid >= MT_ - U) {                      // b1 (threads at the far end: the W1 loop keeps the low threads busy)
+            const int n = tid - (MT_ - U);
+            float g = 0.0f;
+            for (int b = 0; b < NB; ++b) g += d1o[n * BP + b];
+            float* p = b1o + n;
+            *p = adam_apply(g, *p, Mo + (p - sm), Vo + (p - sm), ck);
+        }
+        if (tid < U) { float* p = W3o + tid; *p = adam_apply(g_small, *p, Mo + (p - sm), Vo + (p - sm), ck); }
+        else if (tid < 2 * U) { float* p = b2o + (tid - U); *p = adam_apply(g_small, *p, Mo + (p - sm), Vo + (p - sm), ck); }
+        else if (tid == 2 * U) { float* p = b3r; *p = adam_apply(g_small, *p, Mo + (p - sm), Vo + (p - sm), ck); }
+        __syncthreads();                           // W1 wgrad reads of xT are done before the next minibatch lands
         if (s + 1 < a.steps) commit();
         __syncthreads();
         MP_PROF(6);
@@ -335,6 +392,7 @@ __global__ void __launch_bounds__(MT_, 1) vf_fit_mp_kernel(const MpArgs a) {
         const int j = nat_index(p);
         if (j >= 0 && (j != ob3 || c == 0)) { a.w[j] = W1o[p]; a.m[j] = Mo[p]; a.v[j] = Vo[p]; }
     }
+    cluster_sync_relacq();                         // nobody exits while a peer might still be storing into it
 }
 
 // fp32 feature matrix of the whole batch, in the reference's dtypes: fp64 feature map, then .astype(float32)
@@ -370,15 +428,16 @@ __global__ void mp_adam_consts_kernel(float2* out, int steps, long long step0, f
 }
 
 size_t mp_smem_bytes(int K, int H1, int H2, int C) {
-    const int u1 = H1 / C, u2 = H2 / C, W2P = H1 + 4;
-    const int np = u1 * K + u1 + u2 * W2P + 2 * u2 + 1, npp = round_up(np, 4);
-    const size_t fl = 3 * (size_t)npp + (size_t)(K + H1 + 3 * u1 + u2) * BP + (size_t)(C - 1) * u1 * BP + (size_t)C * NB + MT_ * 4 + 2 * NB + 64;
+    const int H = H1, U = H / C, W2P = H + 4;
+    const int np = U * K + U + U * W2P + 2 * U + 1, npp = round_up(np, 4);
+    const size_t fl = 3 * (size_t)npp + (size_t)(K + 3 * U) * BP + MT_ * 4 + 2 * NB + 2 * (size_t)H * BP + 2 * (size_t)C * U * BP +
+                      2 * (size_t)C * NB + 64;
     return fl * 4;
 }
 
-template <int C>
+template <int C, int H>
 cudaError_t launch_mp(const MpArgs& a, size_t smem, cudaStream_t s) {
-    auto kern = vf_fit_mp_kernel<C>;
+    auto kern = vf_fit_mp_kernel<C, H>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (C > 8) {
@@ -402,13 +461,8 @@ void vf_mp_set_prof(long long* dev16) { g_mp_prof = dev16; }
 
 bool vf_mp_supported(int K, int H1, int H2, int batch, int C) {
     if (batch != NB || (C != 8 && C != 16)) return false;
-    if (H1 % C || H2 % C || H1 > 256 || H2 > 256) return false;
-    const int u1 = H1 / C, u2 = H2 / C;
-    if (NB * K > 4 * MT_) return false;                       // gather prefetch registers
-    if (MT_ % (u2 * 16) || (MT_ / (u2 * 16)) < 1 || H1 % (MT_ / (u2 * 16))) return false;   // layer-2 k-split mapping
-    if (MT_ % H1 || (u2 + MT_ / H1 - 1) / (MT_ / H1) > 4) return false;                     // wgrad W2 mapping
-    if (H1 * 4 % MT_ && H1 * 4 > MT_) return false;
-    if (2 * u2 + 1 > MT_ || u1 < 1) return false;
+    if (H1 != H2 || (H1 != 128 && H1 != 64)) return false;    // instantiated widths (the reference default is 128)
+    if (NB * K > 4 * MT_) return false;                       // gather prefetch registers (K <= 32)
     return mp_smem_bytes(K, H1, H2, C) <= 200 * 1024;
 }
 
@@ -434,7 +488,9 @@ cudaError_t launch_vf_fit_mp(const VfFitArgs& v, const float* feat, const float*
     a.lr = v.lr; a.reg = v.reg; a.beta1 = v.beta1; a.beta2 = v.beta2; a.eps = v.eps;
     a.w = v.w; a.m = v.m; a.v = v.v; a.consts = consts; a.prof = g_mp_prof;
     const size_t smem = mp_smem_bytes(v.K, v.H1, v.H2, C);
-    cudaError_t e = (C == 8) ? launch_mp<8>(a, smem, s) : (C == 16 ? launch_mp<16>(a, smem, s) : cudaErrorInvalidValue);
+    cudaError_t e = cudaErrorInvalidValue;
+    if (v.H1 == 128) e = (C == 8) ? launch_mp<8, 128>(a, smem, s) : launch_mp<16, 128>(a, smem, s);
+    else if (v.H1 == 64) e = (C == 8) ? launch_mp<8, 64>(a, smem, s) : launch_mp<16, 64>(a, smem, s);
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
