@@ -53,7 +53,7 @@ constexpr int S_RING = S_DYLO + 128 * 16 * 2;
 constexpr int S_F32 = S_RING + 2 * CHUNK;
 // fp32 area (floats)
 constexpr int SF_W3 = 0, SF_V3 = 1024, SF_B1 = 2048, SF_B2 = 2176, SF_C1 = 2304, SF_C2 = 2432, SF_B3 = 2560, SF_C3 = 2568,
-              SF_FAC = 2576, SF_YSC = 2592, SF_DYS = SF_YSC + 2 * 128 * 8, SF_GB3 = SF_DYS + 128 * 8, SF_END = SF_GB3 + 32;
+              SF_FAC = 2576, SF_YSC = 2592, SF_DYS = SF_YSC + 4 * 128 * 8, SF_GB3 = SF_DYS + 128 * 8, SF_END = SF_GB3 + 32;
 constexpr int S_BAR = S_F32 + SF_END * 4;
 constexpr int S_TOTAL = S_BAR + 64;
 
@@ -74,14 +74,19 @@ __device__ __forceinline__ void split16(float v, __half& hi, __half& lo) {
     lo = __float2half_rn(v - __half2float(hi));
 }
 
-// write 32 consecutive columns [c0, c0+32) of row m (fp32 values) as fp16 hi / lo into a core-tiled buffer pair
-__device__ __forceinline__ void store_split32(unsigned char* smem, int off_hi, int off_lo, int m, int c0, const float (&v)[32]) {
+// write 16 consecutive columns [c0, c0+16) of row m (fp32 values) as fp16 hi / lo into a core-tiled buffer pair
+__device__ __forceinline__ void store_split16(unsigned char* smem, int off_hi, int off_lo, int m, int c0, const float (&v)[16]) {
     const int rowoff = (m >> 3) * 128 + (m & 7) * 16;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        __half h[8], l[8];
+    for (int g = 0; g < 2; ++g) {
+        __half2 h[4], l[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) split16(v[8 * g + j], h[j], l[j]);
+        for (int j = 0; j < 4; ++j) {
+            const float a = v[8 * g + 2 * j], b = v[8 * g + 2 * j + 1];
+            h[j] = __floats2half2_rn(a, b);                       // one cvt.rn.f16x2.f32 for two values
+            const float2 back = __half22float2(h[j]);
+            l[j] = __floats2half2_rn(a - back.x, b - back.y);
+        }
         const int o = ((c0 >> 3) + g) * LBY + rowoff;
         *reinterpret_cast<uint4*>(smem + off_hi + o) = *reinterpret_cast<const uint4*>(h);
         *reinterpret_cast<uint4*>(smem + off_lo + o) = *reinterpret_cast<const uint4*>(l);
@@ -95,13 +100,13 @@ __device__ __forceinline__ void mma3(uint32_t d, uint64_t a_hi, uint64_t a_lo, u
     mma_f16(d, a_hi, b_lo, idesc, true);
 }
 
-__global__ void __launch_bounds__(256, 1) fvp_tc_kernel(const TcFvpArgs a) {
+__global__ void __launch_bounds__(512, 1) fvp_tc_kernel(const TcFvpArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     float* sf = reinterpret_cast<float*>(smem + S_F32);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S_BAR);     // [0] mma done, [1..2] ring full, [3..4] ring empty
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q = warp & 3, hf = warp >> 2;                          // TMEM lane quadrant, column half
+    const int q = warp & 3, cq = warp >> 2;                          // TMEM lane quadrant, column quarter (32 columns)
     const int m = 32 * q + lane;                                     // sample row of this thread inside the tile
     const int A = a.A;
 
@@ -112,7 +117,7 @@ __global__ void __launch_bounds__(256, 1) fvp_tc_kernel(const TcFvpArgs a) {
         mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
         mbar_init(&bars[3], 1); mbar_init(&bars[4], 1);
     }
-    for (int i = tid; i < (S_RING - S_PHI) / 16; i += 256) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < (S_RING - S_PHI) / 16; i += 512) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     if (tid < 128) {                                                 // ones column (feature 128) of P: carries d/db2 through G2
         const __half one = __float2half_rn(1.0f);
@@ -121,7 +126,7 @@ __global__ void __launch_bounds__(256, 1) fvp_tc_kernel(const TcFvpArgs a) {
     {   // fp32 side tables
         const float* pf = reinterpret_cast<const float*>(a.P + G_F32);
         const float* tf = reinterpret_cast<const float*>(a.T + G_F32);
-        for (int i = tid; i < 1024; i += 256) { sf[SF_W3 + i] = pf[F_W3 + i]; sf[SF_V3 + i] = tf[F_W3 + i]; }
+        for (int i = tid; i < 1024; i += 512) { sf[SF_W3 + i] = pf[F_W3 + i]; sf[SF_V3 + i] = tf[F_W3 + i]; }
         if (tid < 128) { sf[SF_B1 + tid] = pf[F_B1 + tid]; sf[SF_B2 + tid] = pf[F_B2 + tid]; sf[SF_C1 + tid] = tf[F_B1 + tid]; sf[SF_C2 + tid] = tf[F_B2 + tid]; }
         if (tid < 8) {
             sf[SF_B3 + tid] = pf[F_B3 + tid]; sf[SF_C3 + tid] = tf[F_B3 + tid];
@@ -172,7 +177,7 @@ __global__ void __launch_bounds__(256, 1) fvp_tc_kernel(const TcFvpArgs a) {
         const long long base = tile * TM;
         const bool first = (it == 0);
         // ================= P0: stage the input tile (transform, split) =================
-        for (int f = tid; f < TM * a.obs_dim; f += 256) {
+        for (int f = tid; f < TM * a.obs_dim; f += 512) {
             const int r = f / a.obs_dim, k = f - r * a.obs_dim;
             const long long row = base + r;
             float v = 0.0f;
@@ -211,20 +216,20 @@ __global__ void __launch_bounds__(256, 1) fvp_tc_kernel(const TcFvpArgs a) {
         // ================= P2: h1 = tanh(z1+b1) -> P ; hd1 = (1-h1^2)(zd1+c1) -> Q =================
 #pragma unroll 1
         for (int cc = 0; cc < 2; ++cc) {
-            const int c0 = 64 * hf + 32 * cc;
-            uint32_t z[32], zd[32];
-            tmem_ld32(tmem + tlane + T_D1 + c0, z);
-            tmem_ld32(tmem + tlane + T_D2 + c0, zd);
+            const int c0 = 32 * cq + 16 * cc;
+            uint32_t z[16], zd[16];
+            tmem_ld16(tmem + tlane + T_D1 + c0, z);
+            tmem_ld16(tmem + tlane + T_D2 + c0, zd);
             tmem_ld_wait();
-            float h[32], hd[32];
+            float h[16], hd[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 16; ++j) {
                 const float hv = tanhf(__uint_as_float(z[j]) + sf[SF_B1 + c0 + j]);
                 h[j] = hv;
                 hd[j] = (1.0f - hv * hv) * (__uint_as_float(zd[j]) + sf[SF_C1 + c0 + j]);
             }
-            store_split32(smem, S_PHI, S_PLO, m, c0, h);
-            store_split32(smem, S_QHI, S_QLO, m, c0, hd);
+            store_split16(smem, S_PHI, S_PLO, m, c0, h);
+            store_split16(smem, S_QHI, S_QLO, m, c0, hd);
         }
         fence_proxy_async();
         tcgen05_fence_before();
@@ -260,14 +265,14 @@ __global__ void __launch_bounds__(256, 1) fvp_tc_kernel(const TcFvpArgs a) {
             for (int i = 0; i < 8; ++i) yacc[i] = 0.0f;
 #pragma unroll 1
             for (int cc = 0; cc < 2; ++cc) {
-                const int c0 = 64 * hf + 32 * cc;
-                uint32_t z[32], zd[32];
-                tmem_ld32(tmem + tlane + T_D1 + c0, z);
-                tmem_ld32(tmem + tlane + T_D2 + c0, zd);
+                const int c0 = 32 * cq + 16 * cc;
+                uint32_t z[16], zd[16];
+                tmem_ld16(tmem + tlane + T_D1 + c0, z);
+                tmem_ld16(tmem + tlane + T_D2 + c0, zd);
                 tmem_ld_wait();
-                float h[32];
+                float h[16];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
+                for (int j = 0; j < 16; ++j) {
                     const int n = c0 + j;
                     const float hv = tanhf(__uint_as_float(z[j]) + sf[SF_B2 + n]);
                     const float hdv = (1.0f - hv * hv) * (__uint_as_float(zd[j]) + sf[SF_C2 + n]);
@@ -277,21 +282,22 @@ __global__ void __launch_bounds__(256, 1) fvp_tc_kernel(const TcFvpArgs a) {
                     for (int i = 0; i < 8; ++i)
                         if (i < A) yacc[i] = fmaf(hdv, sf[SF_W3 + i * 128 + n], fmaf(hv, sf[SF_V3 + i * 128 + n], yacc[i]));
                 }
-                tmem_st32(tmem + tlane + T_D1 + c0, z);               // keep h2 (fp32) in TMEM for the delta2 epilogue
-                store_split32(smem, S_QHI, S_QLO, m, c0, h);
+                tmem_st16(tmem + tlane + T_D1 + c0, z);               // keep h2 (fp32) in TMEM for the delta2 epilogue
+                store_split16(smem, S_QHI, S_QLO, m, c0, h);
             }
             tmem_st_wait();
 #pragma unroll
-            for (int i = 0; i < 8; ++i) sf[SF_YSC + (hf * 128 + m) * 8 + i] = yacc[i];
+            for (int i = 0; i < 8; ++i) sf[SF_YSC + (cq * 128 + m) * 8 + i] = yacc[i];
         }
         __syncthreads();
-        if (hf == 0) {
+        if (cq == 0) {
             const bool valid = (base + m) < a.n;
             __half dh[8], dl[8];
             float dyv[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                float y = sf[SF_YSC + m * 8 + i] + sf[SF_YSC + (128 + m) * 8 + i] + sf[SF_C3 + i];
+                float y = (sf[SF_YSC + m * 8 + i] + sf[SF_YSC + (128 + m) * 8 + i]) +
+                          (sf[SF_YSC + (256 + m) * 8 + i] + sf[SF_YSC + (384 + m) * 8 + i]) + sf[SF_C3 + i];
                 y = (valid && i < A) ? sf[SF_FAC + i] * y : 0.0f;
                 dyv[i] = y;
                 sf[SF_DYS + m * 8 + i] = y;
@@ -326,13 +332,13 @@ __global__ void __launch_bounds__(256, 1) fvp_tc_kernel(const TcFvpArgs a) {
             for (int i = 0; i < 8; ++i) dyr[i] = sf[SF_DYS + m * 8 + i];
 #pragma unroll 1
             for (int cc = 0; cc < 2; ++cc) {
-                const int c0 = 64 * hf + 32 * cc;
-                uint32_t hz[32];
-                tmem_ld32(tmem + tlane + T_D1 + c0, hz);
+                const int c0 = 32 * cq + 16 * cc;
+                uint32_t hz[16];
+                tmem_ld16(tmem + tlane + T_D1 + c0, hz);
                 tmem_ld_wait();
-                float d[32];
+                float d[16];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
+                for (int j = 0; j < 16; ++j) {
                     const int n = c0 + j;
                     const float hv = __uint_as_float(hz[j]);
                     float t = 0.0f;
@@ -341,7 +347,7 @@ __global__ void __launch_bounds__(256, 1) fvp_tc_kernel(const TcFvpArgs a) {
                         if (i < A) t = fmaf(dyr[i], sf[SF_W3 + i * 128 + n], t);
                     d[j] = (1.0f - hv * hv) * t;
                 }
-                store_split32(smem, S_QHI, S_QLO, m, c0, d);
+                store_split16(smem, S_QHI, S_QLO, m, c0, d);
             }
         }
         fence_proxy_async();
@@ -372,26 +378,28 @@ __global__ void __launch_bounds__(256, 1) fvp_tc_kernel(const TcFvpArgs a) {
         // ================= P8: delta1 = (1-h1^2) dh1 -> Q =================
 #pragma unroll 1
         for (int cc = 0; cc < 2; ++cc) {
-            const int c0 = 64 * hf + 32 * cc;
-            uint32_t dz[32];
-            tmem_ld32(tmem + tlane + T_D2 + c0, dz);
+            const int c0 = 32 * cq + 16 * cc;
+            uint32_t dz[16];
+            tmem_ld16(tmem + tlane + T_D2 + c0, dz);
             tmem_ld_wait();
-            float d[32];
+            float d[16];
             const int rowoff = (m >> 3) * 128 + (m & 7) * 16;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+            for (int g = 0; g < 2; ++g) {
                 const int o = ((c0 >> 3) + g) * LBY + rowoff;
                 const uint4 uh = *reinterpret_cast<const uint4*>(smem + S_PHI + o);
                 const uint4 ul = *reinterpret_cast<const uint4*>(smem + S_PLO + o);
-                const __half* hh = reinterpret_cast<const __half*>(&uh);
-                const __half* hl = reinterpret_cast<const __half*>(&ul);
+                const __half2* hh = reinterpret_cast<const __half2*>(&uh);
+                const __half2* hl = reinterpret_cast<const __half2*>(&ul);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float hv = __half2float(hh[j]) + __half2float(hl[j]);
-                    d[8 * g + j] = (1.0f - hv * hv) * __uint_as_float(dz[8 * g + j]);
+                for (int j = 0; j < 4; ++j) {
+                    const float2 a2 = __half22float2(hh[j]), b2 = __half22float2(hl[j]);
+                    const float h0 = a2.x + b2.x, h1v = a2.y + b2.y;
+                    d[8 * g + 2 * j] = (1.0f - h0 * h0) * __uint_as_float(dz[8 * g + 2 * j]);
+                    d[8 * g + 2 * j + 1] = (1.0f - h1v * h1v) * __uint_as_float(dz[8 * g + 2 * j + 1]);
                 }
             }
-            store_split32(smem, S_QHI, S_QLO, m, c0, d);
+            store_split16(smem, S_QHI, S_QLO, m, c0, d);
         }
         fence_proxy_async();
         tcgen05_fence_before();
@@ -412,15 +420,15 @@ __global__ void __launch_bounds__(256, 1) fvp_tc_kernel(const TcFvpArgs a) {
         float* gp = a.gpartial + (size_t)blockIdx.x * a.gstride;
         // G2: lane = n (row of W2), columns k < h1 ; column 128 = d/db2[n]
         for (int cc = 0; cc < 2; ++cc) {
-            const int c0 = 64 * hf + 32 * cc;
-            uint32_t g[32];
-            tmem_ld32(tmem + tlane + T_G2 + c0, g);
+            const int c0 = 32 * cq + 16 * cc;
+            uint32_t g[16];
+            tmem_ld16(tmem + tlane + T_G2 + c0, g);
             tmem_ld_wait();
             if (m < a.h2)
-                for (int j = 0; j < 32; ++j)
+                for (int j = 0; j < 16; ++j)
                     if (c0 + j < a.h1) gp[a.tW2 + m * a.h1 + c0 + j] = __uint_as_float(g[j]);
         }
-        if (hf == 0) {
+        if (cq == 0) {
             uint32_t g[16];
             tmem_ld16(tmem + tlane + T_G2 + 128, g);
             tmem_ld_wait();
@@ -534,7 +542,7 @@ cudaError_t launch_fvp_tc(const PrepLayout& L, const unsigned char* P, const uns
     a.tW1 = L.tW1; a.tb1 = L.tb1; a.tW2 = L.tW2; a.tb2 = L.tb2; a.tW3 = L.tW3; a.tb3 = L.tb3; a.K0 = L.K0; a.h1 = L.h1; a.h2 = L.h2;
     cudaError_t e = cudaFuncSetAttribute(fvp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S_TOTAL);
     if (e != cudaSuccess) return e;
-    fvp_tc_kernel<<<grid, 256, S_TOTAL, s>>>(a);
+    fvp_tc_kernel<<<grid, 512, S_TOTAL, s>>>(a);
     return cudaGetLastError();
 }
 

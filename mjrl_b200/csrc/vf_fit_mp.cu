@@ -271,22 +271,25 @@ __global__ void __launch_bounds__(MT_, 1) vf_fit_mp_kernel(const MpArgs a) {
         }
         __syncthreads();
         const AdamP ck = s_c;
-        // ---- P3: small gradients, delta2 (in place of h2) ----
-        float g_small = 0.0f;                      // thread n<U: gW3[n]; thread U+n: gb2[n] (after delta2); thread 2U: gb3
-        if (tid < U) { for (int b = 0; b < NB; ++b) g_small = fmaf(dy[b], h2o[tid * BP + b], g_small); }
-        else if (tid == 2 * U) { for (int b = 0; b < NB; ++b) g_small += dy[b]; }
-        __syncthreads();
-        if (tid < ITEMS) {
-            const int n = tid % U, q = tid / U;
-            const float w3 = W3o[n];
-            float4 h = *reinterpret_cast<const float4*>(h2o + n * BP + 4 * q);
-            const float4 d = *reinterpret_cast<const float4*>(dy + 4 * q);
-            h.x = h.x > 0.f ? d.x * w3 : 0.f; h.y = h.y > 0.f ? d.y * w3 : 0.f;
-            h.z = h.z > 0.f ? d.z * w3 : 0.f; h.w = h.w > 0.f ? d.w * w3 : 0.f;
-            *reinterpret_cast<float4*>(h2o + n * BP + 4 * q) = h;
+        // ---- P3: small gradients (one warp per owned unit, shuffle reductions), delta2 (in place of h2) ----
+        // warp w < U: gW3[w] = sum_b dy[b] h2[w][b] and, after the ReLU mask, gb2[w] = sum_b delta2[w][b]; warp 0 also gb3
+        float g_w3 = 0.0f, g_b2 = 0.0f, g_b3 = 0.0f;
+        {
+            const int w = tid >> 5, lane = tid & 31;
+            if (w < U) {
+                const float w3 = W3o[w];
+                const float h0 = h2o[w * BP + lane], h1v = h2o[w * BP + 32 + lane];
+                const float d0 = dy[lane], d1 = dy[32 + lane];
+                g_w3 = warp_sum(fmaf(d0, h0, d1 * h1v));
+                const float e0 = h0 > 0.f ? d0 * w3 : 0.f, e1 = h1v > 0.f ? d1 * w3 : 0.f;
+                g_b2 = warp_sum(e0 + e1);
+                __syncwarp();
+                h2o[w * BP + lane] = e0;                    // delta2 in place of h2 (this warp owns the whole row)
+                h2o[w * BP + 32 + lane] = e1;
+            }
+            if (w == 0) g_b3 = warp_sum(dy[lane] + dy[32 + lane]);
         }
         __syncthreads();
-        if (tid >= U && tid < 2 * U) { for (int b = 0; b < NB; ++b) g_small += h2o[(tid - U) * BP + b]; }
         // ---- partial dgrad over my units, scattered to the owners of each h1 unit (E3) ----
 #pragma unroll
         for (int o = tid; o < H * 4; o += MT_) {
@@ -379,9 +382,14 @@ __global__ void __launch_bounds__(MT_, 1) vf_fit_mp_kernel(const MpArgs a) {
             float* p = b1o + n;
             *p = adam_apply(g, *p, Mo + (p - sm), Vo + (p - sm), ck);
         }
-        if (tid < U) { float* p = W3o + tid; *p = adam_apply(g_small, *p, Mo + (p - sm), Vo + (p - sm), ck); }
-        else if (tid < 2 * U) { float* p = b2o + (tid - U); *p = adam_apply(g_small, *p, Mo + (p - sm), Vo + (p - sm), ck); }
-        else if (tid == 2 * U) { float* p = b3r; *p = adam_apply(g_small, *p, Mo + (p - sm), Vo + (p - sm), ck); }
+        if ((tid & 31) == 0) {                     // lane 0 of warp w holds the reduced small gradients of unit w
+            const int w = tid >> 5;
+            if (w < U) {
+                float* p = W3o + w; *p = adam_apply(g_w3, *p, Mo + (p - sm), Vo + (p - sm), ck);
+                float* pb = b2o + w; *pb = adam_apply(g_b2, *pb, Mo + (pb - sm), Vo + (pb - sm), ck);
+            }
+            if (w == 0) { float* p = b3r; *p = adam_apply(g_b3, *p, Mo + (p - sm), Vo + (p - sm), ck); }
+        }
         __syncthreads();                           // W1 wgrad reads of xT are done before the next minibatch lands
         if (s + 1 < a.steps) commit();
         __syncthreads();
