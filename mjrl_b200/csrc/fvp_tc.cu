@@ -69,6 +69,14 @@ struct TcFvpArgs {
     int tW1, tb1, tW2, tb2, tW3, tb3, K0, h1, h2;
 };
 
+// tanh via one ex2 and one rcp: 1 - 2/(exp(2|x|)+1) with the sign restored.  Absolute error ~5e-8 (the same order as
+// the fp32 rounding of values near 1); used only on the tensor-core path, whose operands are rounded to 22 bits anyway.
+__device__ __forceinline__ float tanh_fast(float x) {
+    const float e = __expf(2.0f * fabsf(x));
+    const float t = 1.0f - __fdividef(2.0f, e + 1.0f);
+    return copysignf(t, x);
+}
+
 __device__ __forceinline__ void split16(float v, __half& hi, __half& lo) {
     hi = __float2half_rn(v);
     lo = __float2half_rn(v - __half2float(hi));
@@ -126,7 +134,12 @@ __global__ void __launch_bounds__(512, 1) fvp_tc_kernel(const TcFvpArgs a) {
     {   // fp32 side tables
         const float* pf = reinterpret_cast<const float*>(a.P + G_F32);
         const float* tf = reinterpret_cast<const float*>(a.T + G_F32);
-        for (int i = tid; i < 1024; i += 512) { sf[SF_W3 + i] = pf[F_W3 + i]; sf[SF_V3 + i] = tf[F_W3 + i]; }
+        // packed last-layer table: sf[SF_W3 + n*16 + {0..7}] = W3[a][n], sf[SF_W3 + n*16 + 8 + {0..7}] = V3[a][n]
+        for (int i = tid; i < 1024; i += 512) {
+            const int aa = i / 128, n = i % 128;
+            sf[SF_W3 + n * 16 + aa] = pf[F_W3 + i];
+            sf[SF_W3 + n * 16 + 8 + aa] = tf[F_W3 + i];
+        }
         if (tid < 128) { sf[SF_B1 + tid] = pf[F_B1 + tid]; sf[SF_B2 + tid] = pf[F_B2 + tid]; sf[SF_C1 + tid] = tf[F_B1 + tid]; sf[SF_C2 + tid] = tf[F_B2 + tid]; }
         if (tid < 8) {
             sf[SF_B3 + tid] = pf[F_B3 + tid]; sf[SF_C3 + tid] = tf[F_B3 + tid];
@@ -224,7 +237,7 @@ __global__ void __launch_bounds__(512, 1) fvp_tc_kernel(const TcFvpArgs a) {
             float h[16], hd[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const float hv = tanhf(__uint_as_float(z[j]) + sf[SF_B1 + c0 + j]);
+                const float hv = tanh_fast(__uint_as_float(z[j]) + sf[SF_B1 + c0 + j]);
                 h[j] = hv;
                 hd[j] = (1.0f - hv * hv) * (__uint_as_float(zd[j]) + sf[SF_C1 + c0 + j]);
             }
@@ -274,13 +287,18 @@ __global__ void __launch_bounds__(512, 1) fvp_tc_kernel(const TcFvpArgs a) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int n = c0 + j;
-                    const float hv = tanhf(__uint_as_float(z[j]) + sf[SF_B2 + n]);
+                    const float hv = tanh_fast(__uint_as_float(z[j]) + sf[SF_B2 + n]);
                     const float hdv = (1.0f - hv * hv) * (__uint_as_float(zd[j]) + sf[SF_C2 + n]);
                     h[j] = hv;
                     z[j] = __float_as_uint(hv);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (i < A) yacc[i] = fmaf(hdv, sf[SF_W3 + i * 128 + n], fmaf(hv, sf[SF_V3 + i * 128 + n], yacc[i]));
+                    const float4* wv = reinterpret_cast<const float4*>(sf + SF_W3 + n * 16);
+                    const float4 w0 = wv[0], w1 = wv[1], v0 = wv[2], v1 = wv[3];   // rows >= A are zero
+                    yacc[0] = fmaf(hdv, w0.x, fmaf(hv, v0.x, yacc[0])); yacc[1] = fmaf(hdv, w0.y, fmaf(hv, v0.y, yacc[1]));
+                    yacc[2] = fmaf(hdv, w0.z, fmaf(hv, v0.z, yacc[2])); yacc[3] = fmaf(hdv, w0.w, fmaf(hv, v0.w, yacc[3]));
+                    if (A > 4) {
+                        yacc[4] = fmaf(hdv, w1.x, fmaf(hv, v1.x, yacc[4])); yacc[5] = fmaf(hdv, w1.y, fmaf(hv, v1.y, yacc[5]));
+                        yacc[6] = fmaf(hdv, w1.z, fmaf(hv, v1.z, yacc[6])); yacc[7] = fmaf(hdv, w1.w, fmaf(hv, v1.w, yacc[7]));
+                    }
                 }
                 tmem_st16(tmem + tlane + T_D1 + c0, z);               // keep h2 (fp32) in TMEM for the delta2 epilogue
                 store_split16(smem, S_QHI, S_QLO, m, c0, h);
@@ -341,10 +359,13 @@ __global__ void __launch_bounds__(512, 1) fvp_tc_kernel(const TcFvpArgs a) {
                 for (int j = 0; j < 16; ++j) {
                     const int n = c0 + j;
                     const float hv = __uint_as_float(hz[j]);
-                    float t = 0.0f;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (i < A) t = fmaf(dyr[i], sf[SF_W3 + i * 128 + n], t);
+                    const float4* wv = reinterpret_cast<const float4*>(sf + SF_W3 + n * 16);
+                    const float4 w0 = wv[0];
+                    float t = fmaf(dyr[0], w0.x, fmaf(dyr[1], w0.y, fmaf(dyr[2], w0.z, dyr[3] * w0.w)));
+                    if (A > 4) {
+                        const float4 w1 = wv[1];
+                        t += fmaf(dyr[4], w1.x, fmaf(dyr[5], w1.y, fmaf(dyr[6], w1.z, dyr[7] * w1.w)));
+                    }
                     d[j] = (1.0f - hv * hv) * t;
                 }
                 store_split16(smem, S_QHI, S_QLO, m, c0, d);

@@ -150,26 +150,25 @@ __global__ void __launch_bounds__(MT_, 1) vf_fit_mp_kernel(const MpArgs a) {
     float pre_x[NPF];
     float pre_t = 0.f;
     int r_nxt[NPF], rt_nxt = 0;
+    int e_row[NPF], e_col[NPF];                    // element slot -> (minibatch row, feature), fixed for the whole epoch
+#pragma unroll
+    for (int u = 0; u < NPF; ++u) { const int e = tid + MT_ * u; e_row[u] = (e < NB * K) ? e / K : -1; e_col[u] = e % K; }
     auto load_idx = [&](int s) {
         const int* pidx = a.perm + (size_t)s * NB;
 #pragma unroll
-        for (int u = 0; u < NPF; ++u) { const int e = tid + MT_ * u; r_nxt[u] = (e < NB * K) ? pidx[e / K] : 0; }
+        for (int u = 0; u < NPF; ++u) r_nxt[u] = (e_row[u] >= 0) ? pidx[e_row[u]] : 0;
         rt_nxt = (tid < NB) ? pidx[tid] : 0;
     };
     auto load_vals = [&]() {
 #pragma unroll
-        for (int u = 0; u < NPF; ++u) {
-            const int e = tid + MT_ * u;
-            if (e < NB * K) pre_x[u] = a.feat[(size_t)r_nxt[u] * K + e % K];
-        }
+        for (int u = 0; u < NPF; ++u)
+            if (e_row[u] >= 0) pre_x[u] = a.feat[(size_t)r_nxt[u] * K + e_col[u]];
         if (tid < NB) pre_t = a.ret32[rt_nxt];
     };
     auto commit = [&]() {
 #pragma unroll
-        for (int u = 0; u < NPF; ++u) {
-            const int e = tid + MT_ * u;
-            if (e < NB * K) xT[(e % K) * BP + e / K] = pre_x[u];
-        }
+        for (int u = 0; u < NPF; ++u)
+            if (e_row[u] >= 0) xT[e_col[u] * BP + e_row[u]] = pre_x[u];
         if (tid < NB) tv[tid] = pre_t;
     };
     load_idx(0);
@@ -180,8 +179,11 @@ __global__ void __launch_bounds__(MT_, 1) vf_fit_mp_kernel(const MpArgs a) {
     if (tid == 0) cc_next = a.consts[0];
     cluster_sync_relacq();                         // barriers initialised and buffers zeroed everywhere before any remote store
 
+    // phase profiler: accumulates in shared memory (a global read-modify-write per phase would itself cost ~1k cycles)
+    __shared__ long long s_prof[16];
+    if (tid < 16) s_prof[tid] = 0;
     long long t_last = clock64();
-#define MP_PROF(i) do { if (a.prof && tid == 0 && c == 0) { const long long _t = clock64(); a.prof[i] += _t - t_last; t_last = _t; } } while (0)
+#define MP_PROF(i) do { if (a.prof && tid == 0 && c == 0) { const long long _t = clock64(); s_prof[i] += _t - t_last; t_last = _t; } } while (0)
     for (int s = 0; s < a.steps; ++s) {
         const int par = s & 1;
         const uint32_t ph = (uint32_t)(s >> 1) & 1u;          // phase parity of the barriers of this step parity
@@ -290,10 +292,12 @@ __global__ void __launch_bounds__(MT_, 1) vf_fit_mp_kernel(const MpArgs a) {
             if (w == 0) g_b3 = warp_sum(dy[lane] + dy[32 + lane]);
         }
         __syncthreads();
+        MP_PROF(8);
         // ---- partial dgrad over my units, scattered to the owners of each h1 unit (E3) ----
-#pragma unroll
-        for (int o = tid; o < H * 4; o += MT_) {
-            const int k = o % H, qg = o / H;                   // 4 row-quads per thread
+        // Warp w handles the 8 consecutive h1 units k = 8w..8w+7 (one owner CTA per warp, so every st.async warp
+        // instruction has a single destination): lane -> (k = 8w + lane%8, row-quad q = lane/8 + 4j, j < 4).
+        for (int kb = (tid >> 5) * 8; kb < H; kb += (MT_ >> 5) * 8) {
+            const int k = kb + (tid & 7), ql = (tid & 31) >> 3;
             float4 acc[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -302,7 +306,7 @@ __global__ void __launch_bounds__(MT_, 1) vf_fit_mp_kernel(const MpArgs a) {
                 const float w = W2o[n * W2P + k];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float4 d = *reinterpret_cast<const float4*>(h2o + n * BP + 4 * (4 * qg + j));
+                    const float4 d = *reinterpret_cast<const float4*>(h2o + n * BP + 4 * (ql + 4 * j));
                     acc[j].x = fmaf(d.x, w, acc[j].x); acc[j].y = fmaf(d.y, w, acc[j].y);
                     acc[j].z = fmaf(d.z, w, acc[j].z); acc[j].w = fmaf(d.w, w, acc[j].w);
                 }
@@ -310,8 +314,9 @@ __global__ void __launch_bounds__(MT_, 1) vf_fit_mp_kernel(const MpArgs a) {
             const int r = k / U;
             const uint32_t dst = map_cluster(dg_s + ((int)c * U + k % U) * BP, r), rb = map_cluster(&bars[2][par], r);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) st_async_v4(dst + 4 * (4 * (4 * qg + j)), acc[j], rb);
+            for (int j = 0; j < 4; ++j) st_async_v4(dst + 16 * (ql + 4 * j), acc[j], rb);
         }
+        MP_PROF(9);
         // ---- wgrad of my W2 rows: g[n][k] = sum_b delta2[n][b] h1[k][b]  (kept in registers until the update) ----
         float gw2[4] = {0.f, 0.f, 0.f, 0.f};
         {
@@ -330,6 +335,7 @@ __global__ void __launch_bounds__(MT_, 1) vf_fit_mp_kernel(const MpArgs a) {
                 }
             }
         }
+        MP_PROF(10);
         // Gather for the next step is issued here: nothing below waits on a fence that would stall on these loads.
         if (s + 1 < a.steps) load_vals();
         if (s + 2 < a.steps) load_idx(s + 2);
@@ -375,12 +381,12 @@ __global__ void __launch_bounds__(MT_, 1) vf_fit_mp_kernel(const MpArgs a) {
             float* p = W1o + n * K + k;
             *p = adam_apply(g, *p, Mo + (p - sm), Vo + (p - sm), ck);
         }
-        if (tid >= MT_ - U) {                      // b1 (threads at the far end: the W1 loop keeps the low threads busy)
-            const int n = tid - (MT_ - U);
-            float g = 0.0f;
-            for (int b = 0; b < NB; ++b) g += d1o[n * BP + b];
-            float* p = b1o + n;
-            *p = adam_apply(g, *p, Mo + (p - sm), Vo + (p - sm), ck);
+        {                                          // b1: one warp per owned unit (taken from the far end of the block:
+            const int w = (MT_ >> 5) - 1 - (tid >> 5), lane = tid & 31;   // the W1 loop keeps the low warps busy)
+            if (w < U) {
+                const float g = warp_sum(d1o[w * BP + lane] + d1o[w * BP + 32 + lane]);
+                if (lane == 0) { float* p = b1o + w; *p = adam_apply(g, *p, Mo + (p - sm), Vo + (p - sm), ck); }
+            }
         }
         if ((tid & 31) == 0) {                     // lane 0 of warp w holds the reduced small gradients of unit w
             const int w = tid >> 5;
@@ -395,6 +401,7 @@ __global__ void __launch_bounds__(MT_, 1) vf_fit_mp_kernel(const MpArgs a) {
         __syncthreads();
         MP_PROF(6);
     }
+    if (a.prof && c == 0 && tid < 16) a.prof[tid] += s_prof[tid];
     // ---- write the owned parameters / moments back to the natural layout ----
     for (int p = tid; p < np; p += MT_) {
         const int j = nat_index(p);

@@ -16,8 +16,8 @@ eng.compute_returns(0.995)
 w = (0.1 * rng.randn(eng.vf_d)).astype(np.float32)
 names_dp = ["fwd L1", "fwd L2", "out+dy", "W3 grad+delta2", "dgrad+wgrad W2", "wgrad W1", "cluster sync 1", "reduce+adam",
             "cluster sync 2", "reload+commit"]
-names_mp = ["P1 L1 slice + E1 scatter", "cluster sync 1", "P2 L2 slice + E2", "cluster sync 2", "P3 delta2/dgrad scatter/wgrad",
-            "cluster sync 3", "P4 delta1 + P5 Adam", "-", "-", "-"]
+names_mp = ["P1 L1 slice + E1 scatter", "wait h1 (E1)", "P2 L2 slice + E2", "wait y (E2)", "P3d gather issue (next step)",
+            "wait dgrad (E3)", "P4 delta1 + P5 Adam + commit", "-", "P3a dy, small grads, delta2", "P3b dgrad + E3 scatter", "P3c wgrad W2"]
 for cl, mp in ((16, True), (8, True), (8, False), (16, False)):
     names = names_mp if mp else names_dp
     eng.vf_set_state(w, np.zeros_like(w), np.zeros_like(w), 0)
@@ -31,7 +31,7 @@ for cl, mp in ((16, True), (8, True), (8, False), (16, False)):
     out = (C.c_longlong * 16)()
     eng.lib.mjb_dev_vf_profile(eng.h, out, 0)
     steps = N // 64 - 1
-    tot = sum(out[:10])
+    tot = sum(out[:11])
     print("cluster=%d model_parallel=%s: %.2f us/step wall, %d cycles/step" % (cl, mp, dt / steps * 1e6, tot // steps))
     for i, n in enumerate(names):
         if n == "-":
