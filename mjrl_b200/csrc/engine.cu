@@ -188,7 +188,7 @@ int set_params(mjb_engine* e, ParamSet& ps, const float* theta_src) {
     if (e->linear) launch_prep_linear(ps.theta, e->LL, ps.prep, e->stream);
     else launch_prep_mlp(ps.theta, e->PL, ps.prep, e->stream);
     e->launches += 2;
-    if (e->tc_ok && &ps == &e->pnew) { launch_tc_prep(ps.theta, e->PL, nullptr, e->tc_prep_new, e->stream); e->launches += 1; }
+    if (e->tc_ok && !e->linear && &ps == &e->pnew) { launch_tc_prep(ps.theta, e->PL, nullptr, e->tc_prep_new, e->stream); e->launches += 1; }
     CK(e, cudaGetLastError());
     return 0;
 }
@@ -256,15 +256,20 @@ int fvp_device(mjb_engine* e, const float* v, const int* idx, long long n_idx, f
     if (e->tc_ok && e->tc_on) {
         // tensor-core path: scale v to O(1) (exact power of two), split to fp16 hi/lo, tcgen05 tile kernel
         launch_tc_vscale(v, e->d, e->tc_vscale, e->stream);
-        launch_tc_prep(v, e->PL, e->tc_vscale, e->tc_prep_tan, e->stream);
+        if (e->linear) launch_lin_tc_prep(v, e->cfg.obs_dim, e->A, e->tc_vscale, e->tc_prep_tan, e->stream);
+        else launch_tc_prep(v, e->PL, e->tc_vscale, e->tc_prep_tan, e->stream);
         const int sms = e->num_sms - (e->fit_in_flight ? std::max(e->vf_cluster, 1) : 0);
-        const long long tiles = (n + 127) / 128;
+        const int tile_rows = e->linear ? 64 : 128;
+        const long long tiles = (n + tile_rows - 1) / tile_rows;
         const int grid = (int)std::max<long long>(1, std::min<long long>(tiles, sms));
         CK(e, cudaMemsetAsync(e->gpartial, 0, sizeof(float) * (size_t)grid * e->gstride, e->stream));
         const int slot = (int)(e->fvp_count % mjb_engine::kFvpRing);
         cudaEventRecord(e->fvp_ev[slot][0], e->stream);
-        cudaError_t ce = launch_fvp_tc(e->PL, e->tc_prep_new, e->tc_prep_tan, e->pnew.in_shift, e->pnew.in_scale,
-                                       e->pnew.out_scale, e->obs, idx, n, e->gpartial, e->gstride, grid, e->stream);
+        cudaError_t ce = e->linear
+            ? launch_linear_tc(e->tc_prep_tan, e->pnew.theta, e->pnew.in_shift, e->pnew.in_scale, e->pnew.out_scale, e->obs,
+                               e->cfg.obs_dim, e->A, idx, n, e->gpartial, e->gstride, e->LL.tW, e->LL.tb, e->LL.tLS, grid, e->stream)
+            : launch_fvp_tc(e->PL, e->tc_prep_new, e->tc_prep_tan, e->pnew.in_shift, e->pnew.in_scale,
+                            e->pnew.out_scale, e->obs, idx, n, e->gpartial, e->gstride, grid, e->stream);
         if (ce != cudaSuccess) FAIL(e, std::string("fvp_tc launch: ") + cudaGetErrorString(ce));
         cudaEventRecord(e->fvp_ev[slot][1], e->stream);
         e->fvp_count += 1;
@@ -470,10 +475,11 @@ int mjb_create(const mjb_config* cfg, mjb_engine** out) {
         cudaStreamSynchronize(e->stream);
     }
     ALLOC(e->prep_tan, e->prep_total);
-    e->tc_ok = !e->linear && fvp_tc_supported(e->PL);
+    e->tc_ok = e->linear ? lin_tc_supported(cfg->obs_dim, cfg->act_dim) : fvp_tc_supported(e->PL);
     if (const char* env = getenv("MJRL_B200_TC")) e->tc_on = atoi(env) != 0;
     if (e->tc_ok) {
-        ALLOC(e->tc_prep_new, fvp_tc_prep_bytes()); ALLOC(e->tc_prep_tan, fvp_tc_prep_bytes()); ALLOC(e->tc_vscale, 2);
+        const size_t pb = e->linear ? lin_tc_prep_bytes() : fvp_tc_prep_bytes();
+        ALLOC(e->tc_prep_new, pb); ALLOC(e->tc_prep_tan, pb); ALLOC(e->tc_vscale, 2);
     }
     ALLOC(e->obs, N * O); ALLOC(e->act, N * A); ALLOC(e->rew, N);
     ALLOC(e->path_off, (size_t)cfg->max_paths + 2); ALLOC(e->term, (size_t)cfg->max_paths + 1); ALLOC(e->tstep, N);

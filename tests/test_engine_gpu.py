@@ -284,6 +284,34 @@ def test_tensor_core_fvp_matches_fma_and_oracle(cuda_device):
     th[-m["act_dim"]:] = 0.3 * rng.randn(m["act_dim"])
     eng.set_params(th)
     assert rel(eng.fvp(v, 1e-4), O.fvp(spec, th, obs, v, 1e-4)) < 1e-5
+    # the linear policy has its own tensor-core FVP kernel (HBM-bound path): golden + wide-observation shape
+    for case_obs in (None, 376, 93):
+        if case_obs is None:
+            gl = load_golden("linear_30x200")
+            pl = golden_paths(gl)
+            el = make_engine(gl, cuda_device)
+            th_l = gl["theta0"]
+            specl = O.PolicySpec(gl["meta"]["obs_dim"], gl["meta"]["act_dim"], ())
+        else:
+            pl = O.synthetic_paths(case_obs, 17, 9, 300, seed=3, ragged=True)
+            specl = O.PolicySpec(case_obs, 17, ())
+            th_l = O.init_policy_params(specl, 2)
+            th_l[-17:] = 0.2 * rng.randn(17)
+            from mjrl_b200.engine import Engine
+            el = Engine(case_obs, 17, (), max_samples=4000, max_paths=16)
+            el.set_params(th_l)
+        el.upload_paths(pl)
+        obs_l = np.concatenate([p["observations"] for p in pl])
+        vl = rng.randn(specl.d).astype(np.float32)
+        want = O.fvp(specl, th_l, obs_l, vl, 1e-4)
+        assert el.set_tensor_cores(True) is True
+        assert rel(el.fvp(vl, 1e-4), want) < 1e-5, (case_obs, rel(el.fvp(vl, 1e-4), want))
+        el.set_tensor_cores(False)
+        assert rel(el.fvp(vl, 1e-4), want) < 1e-5
+        el.set_tensor_cores(True)
+        idl = rng.randint(0, el.n, size=el.n // 2).astype(np.int32)
+        assert rel(el.fvp(vl, 1e-4, idx=idl), O.fvp(specl, th_l, obs_l[idl], vl, 1e-4)) < 1e-5
+        el.close()
     # shapes without a tensor-core kernel report it and keep working on the FMA kernels
     g2 = load_golden("swim_40x250")
     e2 = make_engine(g2, cuda_device)
