@@ -359,17 +359,21 @@ def run_gpu(args, cfg, rank, world, local_rank):
                 "frac": fl / t / 1e12 / peaks["tflops_sustained"], "traffic": prof.get("dram_bytes_per_launch")}
     sm_clock = (clk or {}).get("sm_mhz") or 1965.0
     fma_peak = 148 * 128 * 2 * sm_clock * 1e6 / 1e12
-    tc_active = (not linear) and eng.set_tensor_cores(True)
-    kname = ("linear_kernel<AG,MODE_FVP> (fp32 FMA)" if linear else
-             "fvp_tc_kernel (tcgen05 kind::f16, two-term fp16 split = 3 MMAs per logical product, TMEM accumulators)" if tc_active
-             else "mlp_kernel<H,MT,MODE_FVP> (fp32 FMA)")
+    tc_active = bool(eng.set_tensor_cores(True))
+    if linear:
+        kname = ("linear_tc_kernel (tcgen05 kind::f16, M=128 stacked fp16 hi/lo rows, TMEM-resident gradient accumulators)"
+                 if tc_active else "linear_kernel<AG,MODE_FVP> (fp32 FMA)")
+    else:
+        kname = ("fvp_tc_kernel (tcgen05 kind::f16, two-term fp16 split = 3 MMAs per logical product, TMEM accumulators)"
+                 if tc_active else "mlp_kernel<H,MT,MODE_FVP> (fp32 FMA)")
     roof.update({"kernel": kname,
                  "launch_ms": fvp_ms_kernel, "algorithmic_flops_per_launch": fl, "algorithmic_bytes_per_launch": by,
                  "peak_source": peaks["source"] + ("; bf16 dense sustained (kernel timed inside a long step)" if not linear else ""),
                  "hbm_frac": by / t / 1e9 / peaks["hbm_gbs"],
                  "fp32_fma_peak_tflops_at_observed_clock": fma_peak, "frac_of_fp32_fma_peak": fl / t / 1e12 / fma_peak,
                  "executed_tensor_flops_per_launch": (3 * fl if tc_active else 0),
-                 "note": "rank-0 shard; compute-bound shape (SURVEY 8d); launch_ms is the mean CUDA-event time of the FVP launches "
+                 "note": ("rank-0 shard; HBM-bound shape (SURVEY 8d): obs are streamed exactly once per launch; launch_ms"
+                          if linear else "rank-0 shard; compute-bound shape (SURVEY 8d); launch_ms") + " is the mean CUDA-event time of the FVP launches "
                          "inside the timed steps, where the kernel shares the GPU with the concurrent baseline-fit cluster "
                          "(132 of 148 SMs); achieved counts ALGORITHMIC flops (10P-4P1 per timestep), not the 3x split MMAs"})
 

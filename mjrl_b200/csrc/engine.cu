@@ -56,6 +56,7 @@ struct ParamSet {           // one policy parameter set on device
     float* theta = nullptr;       // flat, reference layout
     float* prep = nullptr;        // kernel layout
     float* in_shift = nullptr; float* in_scale = nullptr; float* out_shift = nullptr; float* out_scale = nullptr;
+    bool in_ident = true;         // in_shift == 0 and in_scale == 1 (the reference's default): kernels may skip the transform
 };
 
 }  // namespace
@@ -266,8 +267,8 @@ int fvp_device(mjb_engine* e, const float* v, const int* idx, long long n_idx, f
         const int slot = (int)(e->fvp_count % mjb_engine::kFvpRing);
         cudaEventRecord(e->fvp_ev[slot][0], e->stream);
         cudaError_t ce = e->linear
-            ? launch_linear_tc(e->tc_prep_tan, e->pnew.theta, e->pnew.in_shift, e->pnew.in_scale, e->pnew.out_scale, e->obs,
-                               e->cfg.obs_dim, e->A, idx, n, e->gpartial, e->gstride, e->LL.tW, e->LL.tb, e->LL.tLS, grid, e->stream)
+            ? launch_linear_tc(e->tc_prep_tan, e->pnew.theta, e->pnew.in_shift, e->pnew.in_scale, e->pnew.out_scale,
+                               e->pnew.in_ident, e->obs, e->cfg.obs_dim, e->A, idx, n, e->gpartial, e->gstride, e->LL.tW, e->LL.tb, e->LL.tLS, grid, e->stream)
             : launch_fvp_tc(e->PL, e->tc_prep_new, e->tc_prep_tan, e->pnew.in_shift, e->pnew.in_scale,
                             e->pnew.out_scale, e->obs, idx, n, e->gpartial, e->gstride, grid, e->stream);
         if (ce != cudaSuccess) FAIL(e, std::string("fvp_tc launch: ") + cudaGetErrorString(ce));
@@ -786,6 +787,13 @@ int mjb_policy_set_transforms(mjb_engine* e, const float* in_shift, const float*
     if (out_shift) CK(e, cudaMemcpyAsync(ps.out_shift, out_shift, A * sizeof(float), cudaMemcpyDefault, e->stream));
     if (out_scale) CK(e, cudaMemcpyAsync(ps.out_scale, out_scale, A * sizeof(float), cudaMemcpyDefault, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
+    if (in_shift || in_scale) {
+        std::vector<float> hs(O), hc(O);
+        CK(e, cudaMemcpy(hs.data(), ps.in_shift, O * sizeof(float), cudaMemcpyDeviceToHost));
+        CK(e, cudaMemcpy(hc.data(), ps.in_scale, O * sizeof(float), cudaMemcpyDeviceToHost));
+        ps.in_ident = true;
+        for (size_t i = 0; i < O; ++i) ps.in_ident = ps.in_ident && hs[i] == 0.0f && hc[i] == 1.0f;
+    }
     e->transforms_equal = false;       // conservative: the reference updates only policy.model (A10)
     e->old_equals_new = false;
     if (which_old) e->old_cache_valid = false;
@@ -1081,6 +1089,17 @@ int mjb_dev_vf_profile(mjb_engine* e, long long* out16, int enable) {
     CK(e, cudaStreamSynchronize(e->stream));
     CK(e, cudaMemcpy(out16, dev, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
     vf_cluster_set_prof(nullptr); vf_mp_set_prof(nullptr);
+    return 0;
+}
+
+// Developer aid: per-phase cycle counters of the tensor-core linear-policy FVP kernel (summed over CTAs).
+int mjb_dev_lin_profile(mjb_engine* e, long long* out8, int enable) {
+    static unsigned long long* dev = nullptr;
+    if (!dev) { CK(e, cudaMalloc(&dev, 8 * sizeof(long long))); }
+    if (enable) { CK(e, cudaMemset(dev, 0, 8 * sizeof(long long))); lin_tc_set_prof(dev); return 0; }
+    CK(e, cudaStreamSynchronize(e->stream));
+    CK(e, cudaMemcpy(out8, dev, 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    lin_tc_set_prof(nullptr);
     return 0;
 }
 

@@ -96,10 +96,11 @@ cudaError_t launch_fvp_tc(const PrepLayout& L, const unsigned char* P, const uns
 // ---- linear_tc.cu : tcgen05 Fisher-vector product of the linear policy (HBM-bound path)
 size_t lin_tc_prep_bytes();
 bool lin_tc_supported(int K0, int A);
+void lin_tc_set_prof(unsigned long long* p);
 void launch_lin_tc_prep(const float* v, int K0, int A, const float* scale_dev, unsigned char* out, cudaStream_t s);
 cudaError_t launch_linear_tc(const unsigned char* T, const float* theta, const float* in_shift, const float* in_scale,
-                             const float* out_scale, const float* obs, int K0, int A, const int* idx, long long n,
-                             float* gpartial, long long gstride, int tW, int tb, int tLS, int grid, cudaStream_t s);
+                             const float* out_scale, bool identity_in, const float* obs, int K0, int A, const int* idx,
+                             long long n, float* gpartial, long long gstride, int tW, int tb, int tLS, int grid, cudaStream_t s);
 
 // ---- vf_fit.cu : sequential minibatch Adam of the value net
 struct VfFitArgs {

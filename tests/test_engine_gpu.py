@@ -311,6 +311,15 @@ def test_tensor_core_fvp_matches_fma_and_oracle(cuda_device):
         el.set_tensor_cores(True)
         idl = rng.randint(0, el.n, size=el.n // 2).astype(np.int32)
         assert rel(el.fvp(vl, 1e-4, idx=idl), O.fvp(specl, th_l, obs_l[idl], vl, 1e-4)) < 1e-5
+        if case_obs is not None:     # non-identity observation / action transforms (the kernel's general path)
+            tr = dict(in_shift=0.3 * rng.randn(case_obs), in_scale=0.5 + rng.rand(case_obs),
+                      out_shift=0.1 * rng.randn(17), out_scale=0.5 + rng.rand(17))
+            spect = O.PolicySpec(case_obs, 17, (), **tr)
+            el.set_transforms(**{k: v.astype(np.float32) for k, v in tr.items()})
+            want_t = O.fvp(spect, th_l, obs_l, vl, 1e-4)
+            assert rel(el.fvp(vl, 1e-4), want_t) < 1e-5
+            el.set_tensor_cores(False)
+            assert rel(el.fvp(vl, 1e-4), want_t) < 1e-5
         el.close()
     # shapes without a tensor-core kernel report it and keep working on the FMA kernels
     g2 = load_golden("swim_40x250")
