@@ -374,8 +374,8 @@ def run_gpu(args, cfg, rank, world, local_rank):
                  "executed_tensor_flops_per_launch": (3 * fl if tc_active else 0),
                  "note": ("rank-0 shard; HBM-bound shape (SURVEY 8d): obs are streamed exactly once per launch; launch_ms"
                           if linear else "rank-0 shard; compute-bound shape (SURVEY 8d); launch_ms") + " is the mean CUDA-event time of the FVP launches "
-                         "inside the timed steps, where the kernel shares the GPU with the concurrent baseline-fit cluster "
-                         "(132 of 148 SMs); achieved counts ALGORITHMIC flops (10P-4P1 per timestep), not the 3x split MMAs"})
+                         "inside the timed steps, where the kernel shares the GPU with the concurrent baseline fit "
+                         "(tensor-core fit kernel: 1 SM, FVP on 147; cluster fallback: 16 SMs); achieved counts ALGORITHMIC flops (10P-4P1 per timestep), not the 3x split MMAs"})
 
     # ---------------- CPU baseline (bounded sample, rank 0, N=1 only) ----------------
     cpu = None

@@ -161,11 +161,14 @@ int  mjb_vf_fit(mjb_engine* e, const int32_t* perms, int epochs, int batch_size,
 int  mjb_vf_fit_begin(mjb_engine* e, const int32_t* perms, int epochs, int batch_size, float lr, float reg_coef,
                       double* err_before);
 int  mjb_vf_fit_end(mjb_engine* e, double* err_after);
-/* Execution shape of the fit.  cluster_ctas 8 or 16 = one thread-block cluster of that many CTAs:
- *   model_parallel = 1 (default, 16 CTAs): hidden units split over the cluster -- weights and Adam moments stay in
- *                      their owner's shared memory, activation slices cross distributed shared memory;
+/* Execution shape of the fit.
+ * cluster_ctas 1 (default) = the single-SM tcgen05 kernel (128x128 hidden, <= 32 input features, batch 64); shapes
+ *   it does not cover fall back to the 16-CTA cluster kernels automatically.
+ * cluster_ctas 8 or 16 = one thread-block cluster of that many CTAs:
+ *   model_parallel = 1: hidden units split over the cluster -- weights and Adam moments stay in their owner's
+ *                      shared memory, activation slices cross distributed shared memory;
  *   model_parallel = 0: minibatch rows split over the cluster, gradients exchanged through L2;
- * cluster_ctas 0 = single-CTA kernel (also the automatic fallback for shapes the cluster kernels do not cover). */
+ * cluster_ctas 0 = single-CTA fp32-FMA kernel (also the last fallback for shapes no other kernel covers). */
 int  mjb_vf_set_cluster(mjb_engine* e, int cluster_ctas, int model_parallel);
 
 /* ---- introspection for benchmarks ------------------------------------------------------------ */

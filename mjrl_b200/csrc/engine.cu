@@ -109,7 +109,8 @@ struct mjb_engine {
     long long vf_step = 0;
     float* vf_cl_scratch = nullptr;
     float* vf_feat = nullptr; float* vf_ret32 = nullptr; long long vf_feat_cap = 0;   // fp32 features / targets of the fit
-    int vf_cluster = 16;      // cluster size of the fit kernel (0 = single-CTA kernel)
+    int vf_cluster = 1;       // fit kernel: 1 = single-SM tensor-core kernel, 8/16 = cluster kernels, 0 = single-CTA FMA kernel
+    int vf_sms = 1;           // SMs the fit kernel in flight occupies (set at launch)
     int vf_model_parallel = 1; // 1: hidden units split over the cluster (vf_fit_mp.cu); 0: minibatch rows split (vf_fit_cluster.cu)
     int* perm_dev = nullptr; long long perm_cap = 0;
     // global (all-rank) copies used by the replicated fit when world_size > 1
@@ -213,7 +214,7 @@ int run_policy(mjb_engine* e, int mode, const ParamSet& ps, const float* tangent
     const int MT = e->linear ? 128 : mlp_tile_rows_for(e->H);
     const long long tiles = (n + MT - 1) / MT;
     // while the fit cluster is running on its own stream it owns vf_cluster SMs: size the persistent grid for the rest
-    const int sms = e->num_sms - (e->fit_in_flight ? std::max(e->vf_cluster, 1) : 0);
+    const int sms = e->num_sms - (e->fit_in_flight ? e->vf_sms : 0);
     int grid = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)e->occ[mode] * sms));
     grid = std::min(grid, e->max_grid);
     if (bwd) CK(e, cudaMemsetAsync(e->gpartial, 0, sizeof(float) * (size_t)grid * e->gstride, e->stream));
@@ -259,7 +260,7 @@ int fvp_device(mjb_engine* e, const float* v, const int* idx, long long n_idx, f
         launch_tc_vscale(v, e->d, e->tc_vscale, e->stream);
         if (e->linear) launch_lin_tc_prep(v, e->cfg.obs_dim, e->A, e->tc_vscale, e->tc_prep_tan, e->stream);
         else launch_tc_prep(v, e->PL, e->tc_vscale, e->tc_prep_tan, e->stream);
-        const int sms = e->num_sms - (e->fit_in_flight ? std::max(e->vf_cluster, 1) : 0);
+        const int sms = e->num_sms - (e->fit_in_flight ? e->vf_sms : 0);
         const int tile_rows = e->linear ? 64 : 128;
         const long long tiles = (n + tile_rows - 1) / tile_rows;
         const int grid = (int)std::max<long long>(1, std::min<long long>(tiles, sms));
@@ -1014,9 +1015,13 @@ static int vf_fit_launch(mjb_engine* e, const int32_t* perms, int epochs, int ba
     a.obs = fobs; a.tstep = ftstep; a.returns = fret; a.n = N;
     a.steps = steps; a.batch = batch_size; a.lr = lr; a.reg = reg_coef; a.beta1 = 0.9f; a.beta2 = 0.999f; a.eps = 1e-8f;
     a.w = e->vf_w; a.m = e->vf_m; a.v = e->vf_v; a.wT = e->vf_wT; a.loss_out = nullptr;
-    const bool use_mp = e->vf_cluster > 0 && e->vf_model_parallel && vf_mp_supported(a.K, a.H1, a.H2, a.batch, e->vf_cluster);
-    const bool use_dp = !use_mp && e->vf_cluster > 0 && vf_cluster_supported(a.K, a.H1, a.H2, a.batch, e->vf_cluster);
-    if (use_mp) {
+    // 1 (the default) asks for the tensor-core kernel; shapes it does not cover fall back to the 16-CTA cluster kernels
+    const bool use_tc = e->vf_cluster == 1 && vf_tc_supported(a.K, a.H1, a.H2, a.batch);
+    const int ccl = (e->vf_cluster == 1 && !use_tc) ? 16 : e->vf_cluster;
+    const bool use_mp = !use_tc && ccl > 1 && e->vf_model_parallel && vf_mp_supported(a.K, a.H1, a.H2, a.batch, ccl);
+    const bool use_dp = !use_tc && !use_mp && ccl > 1 && vf_cluster_supported(a.K, a.H1, a.H2, a.batch, ccl);
+    e->vf_sms = (use_mp || use_dp) ? ccl : 1;
+    if (use_mp || use_tc) {
         if (N > e->vf_feat_cap) {
             if (e->vf_feat) { cudaFree(e->vf_feat); cudaFree(e->vf_ret32); }
             e->vf_feat_cap = N;
@@ -1033,8 +1038,9 @@ static int vf_fit_launch(mjb_engine* e, const int32_t* perms, int epochs, int ba
         a.perm = e->perm_dev + (size_t)ep * N;
         a.step0 = e->vf_step;
         cudaError_t ce;
-        if (use_mp) { ce = launch_vf_fit_mp(a, e->vf_feat, e->vf_ret32, e->vf_cluster, fs); e->launches += 2; }
-        else if (use_dp) { ce = launch_vf_fit_cluster(a, e->vf_cl_scratch, e->vf_cluster, fs); e->launches += 3; }
+        if (use_tc) { ce = launch_vf_fit_tc(a, e->vf_feat, e->vf_ret32, fs); e->launches += 2; }
+        else if (use_mp) { ce = launch_vf_fit_mp(a, e->vf_feat, e->vf_ret32, ccl, fs); e->launches += 2; }
+        else if (use_dp) { ce = launch_vf_fit_cluster(a, e->vf_cl_scratch, ccl, fs); e->launches += 3; }
         else { ce = launch_vf_fit(a, fs); e->launches += 1; }
         if (ce != cudaSuccess) FAIL(e, std::string("vf fit launch (batch<=64, multiple of 4; sizes must fit 220 KB smem): ") + cudaGetErrorString(ce));
         e->vf_step += steps;
@@ -1085,10 +1091,10 @@ int mjb_event_elapsed_ms(mjb_engine* e, int slot_a, int slot_b, float* ms) {
 int mjb_dev_vf_profile(mjb_engine* e, long long* out16, int enable) {
     static long long* dev = nullptr;
     if (!dev) { CK(e, cudaMalloc(&dev, 16 * sizeof(long long))); }
-    if (enable) { CK(e, cudaMemset(dev, 0, 16 * sizeof(long long))); vf_cluster_set_prof(dev); vf_mp_set_prof(dev); return 0; }
+    if (enable) { CK(e, cudaMemset(dev, 0, 16 * sizeof(long long))); vf_cluster_set_prof(dev); vf_mp_set_prof(dev); vf_tc_set_prof(dev); return 0; }
     CK(e, cudaStreamSynchronize(e->stream));
     CK(e, cudaMemcpy(out16, dev, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
-    vf_cluster_set_prof(nullptr); vf_mp_set_prof(nullptr);
+    vf_cluster_set_prof(nullptr); vf_mp_set_prof(nullptr); vf_tc_set_prof(nullptr);
     return 0;
 }
 
@@ -1109,7 +1115,8 @@ int mjb_policy_set_tensor_cores(mjb_engine* e, int on) {
 }
 
 int mjb_vf_set_cluster(mjb_engine* e, int cluster_ctas, int model_parallel) {
-    if (cluster_ctas != 0 && cluster_ctas != 8 && cluster_ctas != 16) FAIL(e, "cluster size must be 0, 8 or 16");
+    if (cluster_ctas != 0 && cluster_ctas != 1 && cluster_ctas != 8 && cluster_ctas != 16)
+        FAIL(e, "cluster size must be 0 (single-CTA FMA), 1 (single-CTA tensor cores), 8 or 16");
     e->vf_cluster = cluster_ctas;
     e->vf_model_parallel = model_parallel != 0;
     return 0;

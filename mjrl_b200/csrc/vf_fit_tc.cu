@@ -1,0 +1,553 @@
+// MLPBaseline.fit on ONE SM with tcgen05 tensor cores (baselines/mlp_baseline.py:61-95, utils/optimize_model.py:7-36).
+//
+// The minibatch-Adam chain is sequential, so the step time is latency.  The cluster kernel (vf_fit_mp.cu) splits the
+// hidden units over 16 SMs and pays three distributed-shared-memory hand-offs per step; this kernel keeps the whole
+// (obs+4) -> 128 -> 128 -> 1 network, its gradients and its optimizer state on one SM and runs the five GEMMs of a
+// step as tcgen05.mma with the HIDDEN UNITS on the M axis (M = 128 is the full-rate shape; the 64-row minibatch is N):
+//
+//   z1^T  [u][n] = W1 [u][k]  x   [n][k]        A = W1  (K-major)   B = X    (K-major)
+//   z2^T  [o][n] = W2 [o][i]  h1^T[i][n]        A = W2  (K-major)   B = h1^T (MN-major)
+//   dh1^T [i][n] = W2 [o][i]  dz2^T[o][n]       A = W2  (MN-major)  B = dz2^T(MN-major)   -- the same W2 buffer
+//   gW2   [o][i] = dz2^T[o][n] h1^T[i][n]       A = dz2^T (K-major) B = h1^T (K-major)    -- the same h1^T buffer
+//   gW1   [u][k] = dz1^T[u][n] x   [n][k]       A = dz1^T (K-major) B = X    (MN-major)   -- the same X buffer
+//
+// All operands are two-term fp16 splits (hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM), written by the epilogue
+// threads in the no-swizzle core-tiled layout of tc_common.cuh: thread (unit u, column quarter) owns a TMEM lane, so
+// it writes whole 16-byte core-matrix rows and nothing is ever transposed.
+// State: W2's fp32 master copy lives in registers (32 per thread), its Adam moments in TMEM (2 x 128 columns), W1's
+// state and the small vectors in shared memory.  512 threads; thread 0 issues the MMAs.
+// Semantics (minibatch order, 1/B scaling, L2-in-gradient weight decay, bias correction, state persistence) are the
+// reference's; sums run in a fixed order (deterministic).
+#include <cuda_fp16.h>
+
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace mjb {
+
+using namespace tc;
+
+namespace {
+
+constexpr int H = 128, NB = 64, KP = 32, NT = 512;
+// Power-of-two operand scales (exact to apply and to undo): they keep the fp16 LOW terms out of the subnormal range,
+// where a two-term split would lose its 22 significant bits (weights ~0.1 -> lo ~5e-5; gradients ~1e-4 -> lo ~5e-8).
+constexpr float SW = 64.0f;                // weights W1, W2
+constexpr float SA = 16.0f;                // activations: features x, hidden h1
+constexpr float SG = 1024.0f;              // back-propagated deltas dz2, dz1
+constexpr int LB128 = 16 * 128;            // column-group stride of buffers with 128 rows
+constexpr int LB64 = 16 * 64;              // ... with 64 rows (X)
+constexpr int W2_BYTES = H * H * 2, W1_BYTES = H * KP * 2, X_BYTES = NB * KP * 2, HT_BYTES = H * NB * 2;
+
+// shared memory map (bytes)
+constexpr int S_W2H = 0, S_W2L = S_W2H + W2_BYTES, S_W1H = S_W2L + W2_BYTES, S_W1L = S_W1H + W1_BYTES;
+constexpr int S_XH = S_W1L + W1_BYTES, S_XL = S_XH + X_BYTES, S_HH = S_XL + X_BYTES, S_HL = S_HH + HT_BYTES;
+constexpr int S_DH = S_HL + HT_BYTES, S_DL = S_DH + HT_BYTES;
+constexpr int S_F32 = S_DL + HT_BYTES;
+// fp32 area (floats)
+constexpr int F_W1W = 0, F_W1M = F_W1W + KP * H, F_W1V = F_W1M + KP * H;       // W1 state, [k][u]
+constexpr int F_VEC = F_W1V + KP * H;                                          // b1,b2,w3: (w,m,v)[128] each -> 9 x 128
+constexpr int F_B3 = F_VEC + 9 * H;                                            // b3 w,m,v (+pad)
+constexpr int F_YP = F_B3 + 4;                                                 // ypart[4][64]
+constexpr int F_GW3 = F_YP + 4 * NB, F_GB2 = F_GW3 + 4 * H, F_GB1 = F_GB2 + 4 * H, F_GB3 = F_GB1 + 4 * H;
+constexpr int F_T = F_GB3 + 4;                                                 // targets t[64]
+constexpr int F_END = F_T + NB;
+constexpr int S_BAR = S_F32 + F_END * 4;
+constexpr int S_TOTAL = S_BAR + 32;
+
+// TMEM columns.  D holds [X*hi | X*lo] halves of the N-concatenated products; gW1 reuses its columns (D is dead by then)
+constexpr uint32_t T_D = 0, T_G1 = 0, T_G2 = 128, T_M = 256, T_V = 384, T_COLS = 512;
+
+struct TcFitArgs {
+    int K, steps;
+    const float* feat; const float* ret32; const int* perm;
+    float reg, beta1, beta2, eps;
+    float* w; float* m; float* v;
+    const float2* consts;                    // per-step {1/sqrt(1-b2^t), -lr/(1-b1^t)}
+    long long* prof;
+};
+
+struct AdamP { float one_m_b1, b2, one_m_b2, rbc2_sqrt, eps, neg_step, reg; };
+
+// torch.optim.Adam update.  One SM updates all 20 k parameters every step, so the square root and the division use
+// the MUFU approximations (<= 2 ulp each, the same order as the two-term fp16 rounding of the GEMM operands).
+__device__ __forceinline__ float adam_apply(float g, float w, float& m, float& v, const AdamP& c) {
+    g = fmaf(c.reg, w, g);
+    m = fmaf(c.one_m_b1, g - m, m);
+    v = fmaf(c.one_m_b2 * g, g, v * c.b2);
+    float sq, rc;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(v));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fmaf(sq, c.rbc2_sqrt, c.eps)));
+    return fmaf(c.neg_step, m * rc, w);
+}
+
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+
+// 8 consecutive fp32 values -> fp16 hi / lo, one 16-byte core-matrix row each
+__device__ __forceinline__ void split8_store(const float (&x)[8], unsigned char* hi, unsigned char* lo) {
+    __half2 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        h[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+        const float2 b = __half22float2(h[j]);
+        l[j] = __floats2half2_rn(x[2 * j] - b.x, x[2 * j + 1] - b.y);
+    }
+    *reinterpret_cast<uint4*>(hi) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(lo) = *reinterpret_cast<const uint4*>(l);
+}
+
+// D (+)= A B^T over `ksteps` 16-element reduction steps with two-term operands (hi*hi + lo*hi + hi*lo)
+__device__ __forceinline__ void gemm3(uint32_t d, uint32_t ah, uint32_t al, uint32_t a_step, uint32_t a_lbo, uint32_t a_sbo,
+                                      uint32_t bh, uint32_t bl, uint32_t b_step, uint32_t b_lbo, uint32_t b_sbo, int ksteps,
+                                      uint32_t idesc) {
+    for (int j = 0; j < ksteps; ++j) {
+        const uint64_t dah = make_desc(ah + j * a_step, a_lbo, a_sbo), dal = make_desc(al + j * a_step, a_lbo, a_sbo);
+        const uint64_t dbh = make_desc(bh + j * b_step, b_lbo, b_sbo), dbl = make_desc(bl + j * b_step, b_lbo, b_sbo);
+        mma_f16(d, dah, dbh, idesc, j > 0);
+        mma_f16(d, dal, dbh, idesc, true);
+        mma_f16(d, dah, dbl, idesc, true);
+    }
+}
+
+// Same product with the B terms N-concatenated: the buffer pair [B hi | B lo] is contiguous along N, so
+//   D[:, 0:n] (+)= A_hi B_hi + A_lo B_hi   and   D[:, n:2n] (+)= A_hi B_lo     -- two MMAs per step instead of three;
+// the epilogue adds the two column halves.
+__device__ __forceinline__ void gemm2c(uint32_t d, uint32_t ah, uint32_t al, uint32_t a_step, uint32_t a_lbo, uint32_t a_sbo,
+                                       uint32_t bh, uint32_t b_step, uint32_t b_lbo, uint32_t b_sbo, int ksteps,
+                                       uint32_t idesc_2n, uint32_t idesc_n) {
+    for (int j = 0; j < ksteps; ++j) {
+        const uint64_t dah = make_desc(ah + j * a_step, a_lbo, a_sbo), dal = make_desc(al + j * a_step, a_lbo, a_sbo);
+        const uint64_t dbh = make_desc(bh + j * b_step, b_lbo, b_sbo);
+        mma_f16(d, dah, dbh, idesc_2n, j > 0);
+        mma_f16(d, dal, dbh, idesc_n, true);
+    }
+}
+
+__global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float* sf = reinterpret_cast<float*>(smem + S_F32);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S_BAR);
+    __shared__ uint32_t s_tmem;
+    __shared__ long long s_prof[16];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, cq = warp >> 2, u = 32 * q + lane;       // TMEM lane = hidden unit u; column quarter cq
+    const int K = a.K;
+    // natural (nn.Sequential) offsets
+    const int oW1 = 0, ob1 = H * K, oW2 = ob1 + H, ob2 = oW2 + H * H, oW3 = ob2 + H, ob3 = oW3 + H;
+
+    if (warp == 0) tmem_alloc(&s_tmem, T_COLS);
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+    if (tid < 16) s_prof[tid] = 0;
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = s_tmem, sbase = smem_u32(smem);
+    const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
+    const uint32_t rowoff = (uint32_t)((u >> 3) * 128 + (u & 7) * 16);      // core-tiled row offset of unit u (rows = 128)
+
+    // ---- load the state ----
+    float w2[32];                                                    // W2[u][32cq .. 32cq+31], fp32 master
+    {
+        uint32_t mv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) w2[j] = a.w[oW2 + u * H + 32 * cq + j];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mv[j] = __float_as_uint(a.m[oW2 + u * H + 32 * cq + j]);
+        tmem_st32(tlane + T_M + 32 * cq, mv);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mv[j] = __float_as_uint(a.v[oW2 + u * H + 32 * cq + j]);
+        tmem_st32(tlane + T_V + 32 * cq, mv);
+        tmem_st_wait();
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+            float x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = SW * w2[8 * c8 + j];
+            const uint32_t o = rowoff + (uint32_t)(4 * cq + c8) * LB128;
+            split8_store(x, smem + S_W2H + o, smem + S_W2L + o);
+        }
+    }
+    {                                                                // W1[u][8cq .. 8cq+7] (zero beyond K)
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = 8 * cq + j;
+            const bool in = k < K;
+            const float wv = in ? a.w[oW1 + u * K + k] : 0.0f;
+            x[j] = SW * wv;
+            sf[F_W1W + k * H + u] = wv;
+            sf[F_W1M + k * H + u] = in ? a.m[oW1 + u * K + k] : 0.0f;
+            sf[F_W1V + k * H + u] = in ? a.v[oW1 + u * K + k] : 0.0f;
+        }
+        const uint32_t o = rowoff + (uint32_t)cq * LB128;
+        split8_store(x, smem + S_W1H + o, smem + S_W1L + o);
+    }
+    if (cq == 0) {                                                   // vectors: b1, b2, w3 (w, m, v)
+        const int offs[3] = {ob1, ob2, oW3};
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            sf[F_VEC + (3 * p + 0) * H + u] = a.w[offs[p] + u];
+            sf[F_VEC + (3 * p + 1) * H + u] = a.m[offs[p] + u];
+            sf[F_VEC + (3 * p + 2) * H + u] = a.v[offs[p] + u];
+        }
+    }
+    if (tid == 0) { sf[F_B3] = a.w[ob3]; sf[F_B3 + 1] = a.m[ob3]; sf[F_B3 + 2] = a.v[ob3]; }
+
+    // ---- minibatch gather pipeline: thread -> (row n, 4 features) ----
+    const int gn = tid >> 3, gk = 4 * (tid & 7);
+    const uint32_t xoff = core_offset(gn, gk, NB);
+    float xr[4] = {0.f, 0.f, 0.f, 0.f};
+    float tt = 0.0f;
+    auto load_rows = [&](int idx) {
+        const float* p = a.feat + (size_t)idx * K + gk;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xr[j] = (gk + j < K) ? p[j] : 0.0f;
+        if (gk == 0) tt = a.ret32[idx];
+    };
+    auto stage_x = [&]() {
+        const float s0 = SA * xr[0], s1 = SA * xr[1], s2 = SA * xr[2], s3 = SA * xr[3];
+        const __half2 h01 = __floats2half2_rn(s0, s1), h23 = __floats2half2_rn(s2, s3);
+        const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(s0 - b01.x, s1 - b01.y), l23 = __floats2half2_rn(s2 - b23.x, s3 - b23.y);
+        uint2 hv, lv;
+        hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+        lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+        *reinterpret_cast<uint2*>(smem + S_XH + xoff) = hv;
+        *reinterpret_cast<uint2*>(smem + S_XL + xoff) = lv;
+        if (gk == 0) sf[F_T + gn] = tt;
+    };
+    int i1 = 0, i2 = 0;
+    load_rows(a.perm[gn]);
+    stage_x();
+    if (a.steps > 1) i1 = a.perm[NB + gn];
+    if (a.steps > 2) i2 = a.perm[2 * NB + gn];
+
+    const uint32_t ID_L1 = make_idesc_f16(128, NB, false, false);
+    const uint32_t ID_L2 = make_idesc_f16(128, NB, false, true), ID_L2c = make_idesc_f16(128, 2 * NB, false, true);
+    const uint32_t ID_DH = make_idesc_f16(128, NB, true, true), ID_DHc = make_idesc_f16(128, 2 * NB, true, true);
+    const uint32_t ID_G2 = make_idesc_f16(128, H, false, false);
+    const uint32_t ID_G1 = make_idesc_f16(128, KP, false, true), ID_G1c = make_idesc_f16(128, 2 * KP, false, true);
+    uint32_t p0 = 0, p1 = 0;
+    auto wait0 = [&]() { mbar_wait(&bars[0], p0); p0 ^= 1; tcgen05_fence_after(); };
+    auto wait1 = [&]() { mbar_wait(&bars[1], p1); p1 ^= 1; tcgen05_fence_after(); };
+    auto sync_ops = [&]() { fence_proxy_async(); tcgen05_fence_before(); __syncthreads(); };
+
+    long long t_last = clock64();
+#define TC_PROF(i) do { if (a.prof && tid == 0) { const long long _t = clock64(); s_prof[i] += _t - t_last; t_last = _t; } } while (0)
+
+    AdamP ap;
+    ap.one_m_b1 = 1.0f - a.beta1; ap.b2 = a.beta2; ap.one_m_b2 = 1.0f - a.beta2; ap.eps = a.eps; ap.reg = a.reg;
+
+    for (int s = 0; s < a.steps; ++s) {
+        sync_ops();                                                  // X(s), weights(s) staged
+        // ===== layer 1: z1^T = W1 x^T =====
+        if (tid == 0) {
+            tcgen05_fence_after();
+            gemm3(tmem + T_D, sbase + S_W1H, sbase + S_W1L, 2 * LB128, LB128, 128,
+                  sbase + S_XH, sbase + S_XL, 2 * LB64, LB64, 128, KP / 16, ID_L1);
+            mma_commit(&bars[0]);
+        }
+        if (s + 1 < a.steps) load_rows(i1);                          // rows of step s+1: a whole step to land
+        i1 = i2;
+        if (s + 3 < a.steps) i2 = a.perm[(size_t)(s + 3) * NB + gn];
+        const float2 cst = a.consts[s];
+        ap.rbc2_sqrt = cst.x; ap.neg_step = cst.y;
+        TC_PROF(0);
+        wait0();
+        TC_PROF(1);
+        uint32_t mask1 = 0;
+        {                                                            // h1 = relu(z1 + b1) -> h1^T operand rows
+            uint32_t z[16];
+            tmem_ld16(tlane + T_D + 16 * cq, z);
+            tmem_ld_wait();
+            const float b = sf[F_VEC + 0 * H + u];
+            float x[8];
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float zz = fmaf(__uint_as_float(z[8 * g + j]), 1.0f / (SW * SA), b);
+                    const bool on = zz > 0.0f;
+                    mask1 |= (on ? 1u : 0u) << (8 * g + j);
+                    x[j] = on ? SA * zz : 0.0f;
+                }
+                const uint32_t o = rowoff + (uint32_t)(2 * cq + g) * LB128;
+                split8_store(x, smem + S_HH + o, smem + S_HL + o);
+            }
+        }
+        sync_ops();
+        TC_PROF(2);
+        // ===== layer 2: z2^T = W2 h1 =====
+        if (tid == 0) {
+            tcgen05_fence_after();
+            gemm2c(tmem + T_D, sbase + S_W2H, sbase + S_W2L, 2 * LB128, LB128, 128,
+                   sbase + S_HH, 2 * 128, 128, LB128, H / 16, ID_L2c, ID_L2);
+            mma_commit(&bars[0]);
+        }
+        TC_PROF(3);
+        wait0();
+        TC_PROF(4);
+        float h2[16];
+        uint32_t mask2 = 0;
+        const float w3u = sf[F_VEC + 6 * H + u];
+        {                                                            // h2 = relu(z2 + b2); partial outputs
+            uint32_t z[16], zl[16];
+            tmem_ld16(tlane + T_D + 16 * cq, z);
+            tmem_ld16(tlane + T_D + NB + 16 * cq, zl);
+            tmem_ld_wait();
+            const float b = sf[F_VEC + 3 * H + u];
+            float p[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float zz = fmaf(__uint_as_float(z[j]) + __uint_as_float(zl[j]), 1.0f / (SW * SA), b);
+                const bool on = zz > 0.0f;
+                mask2 |= (on ? 1u : 0u) << j;
+                h2[j] = on ? zz : 0.0f;
+                p[j] = w3u * h2[j];
+            }
+            // transpose-reduce over the 32 units of this warp: lane ends with the sum for n = 16cq + (lane >> 1)
+#pragma unroll
+            for (int st = 0; st < 4; ++st) {
+                const int half = 8 >> st;                            // values kept after this stage
+                const bool up = (lane >> (4 - st)) & 1;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (i < half) {
+                        const float send = up ? p[i] : p[i + half];
+                        const float keep = up ? p[i + half] : p[i];
+                        p[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16 >> st);
+                    }
+                }
+            }
+            p[0] += __shfl_xor_sync(0xffffffffu, p[0], 1);
+            if ((lane & 1) == 0) sf[F_YP + q * NB + 16 * cq + (lane >> 1)] = p[0];
+        }
+        __syncthreads();
+        TC_PROF(5);
+        {                                                            // dy, small gradients, dz2^T operand rows
+            const float b3 = sf[F_B3];
+            float gw3 = 0.0f, gb2 = 0.0f, gb3 = 0.0f;
+            float x[8];
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const int n0 = 16 * cq + 8 * g;
+                float y[8], tg[8];
+#pragma unroll
+                for (int h4 = 0; h4 < 2; ++h4) {                     // fixed-order sum of the four quadrant partials
+                    const float4 p0 = *reinterpret_cast<const float4*>(sf + F_YP + n0 + 4 * h4);
+                    const float4 p1 = *reinterpret_cast<const float4*>(sf + F_YP + NB + n0 + 4 * h4);
+                    const float4 p2 = *reinterpret_cast<const float4*>(sf + F_YP + 2 * NB + n0 + 4 * h4);
+                    const float4 p3 = *reinterpret_cast<const float4*>(sf + F_YP + 3 * NB + n0 + 4 * h4);
+                    const float4 t4 = *reinterpret_cast<const float4*>(sf + F_T + n0 + 4 * h4);
+                    y[4 * h4 + 0] = (((p0.x + p1.x) + p2.x) + p3.x) + b3; y[4 * h4 + 1] = (((p0.y + p1.y) + p2.y) + p3.y) + b3;
+                    y[4 * h4 + 2] = (((p0.z + p1.z) + p2.z) + p3.z) + b3; y[4 * h4 + 3] = (((p0.w + p1.w) + p2.w) + p3.w) + b3;
+                    tg[4 * h4 + 0] = t4.x; tg[4 * h4 + 1] = t4.y; tg[4 * h4 + 2] = t4.z; tg[4 * h4 + 3] = t4.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float dy = (2.0f / (float)NB) * (y[j] - tg[j]);
+                    gw3 = fmaf(h2[8 * g + j], dy, gw3);
+                    gb3 += dy;
+                    const float dz = ((mask2 >> (8 * g + j)) & 1u) ? dy * w3u : 0.0f;
+                    gb2 += dz;
+                    x[j] = SG * dz;
+                }
+                const uint32_t o = rowoff + (uint32_t)(2 * cq + g) * LB128;
+                split8_store(x, smem + S_DH + o, smem + S_DL + o);
+            }
+            sf[F_GW3 + cq * H + u] = gw3;
+            sf[F_GB2 + cq * H + u] = gb2;
+            if (u == 0) sf[F_GB3 + cq] = gb3;
+        }
+        sync_ops();
+        TC_PROF(6);
+        // ===== backward: dh1^T = W2^T dz2 (bar 0), gW2 = dz2 h1^T (bar 1) =====
+        if (tid == 0) {
+            tcgen05_fence_after();
+            gemm2c(tmem + T_D, sbase + S_W2H, sbase + S_W2L, 2 * 128, 128, LB128,
+                   sbase + S_DH, 2 * 128, 128, LB128, H / 16, ID_DHc, ID_DH);
+            mma_commit(&bars[0]);
+            gemm3(tmem + T_G2, sbase + S_DH, sbase + S_DL, 2 * LB128, LB128, 128,
+                  sbase + S_HH, sbase + S_HL, 2 * LB128, LB128, 128, NB / 16, ID_G2);
+            mma_commit(&bars[1]);
+        }
+        TC_PROF(7);
+        wait0();
+        TC_PROF(8);
+        {                                                            // dz1 = relu'(z1) dh1 -> dz1^T operand rows
+            uint32_t z[16], zl[16];
+            tmem_ld16(tlane + T_D + 16 * cq, z);
+            tmem_ld16(tlane + T_D + NB + 16 * cq, zl);
+            tmem_ld_wait();
+            float x0[8], x1[8];
+            float gb1 = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                // TMEM holds SW*SG*dh1; the operand keeps the SG scale
+                x0[j] = ((mask1 >> j) & 1u) ? (__uint_as_float(z[j]) + __uint_as_float(zl[j])) * (1.0f / SW) : 0.0f;
+                x1[j] = ((mask1 >> (8 + j)) & 1u) ? (__uint_as_float(z[8 + j]) + __uint_as_float(zl[8 + j])) * (1.0f / SW) : 0.0f;
+                gb1 += x0[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gb1 += x1[j];
+            sf[F_GB1 + cq * H + u] = gb1 * (1.0f / SG);
+            wait1();                                                 // gW2 done: the dz buffer is free
+            const uint32_t o = rowoff + (uint32_t)(2 * cq) * LB128;
+            split8_store(x0, smem + S_DH + o, smem + S_DL + o);
+            split8_store(x1, smem + S_DH + o + LB128, smem + S_DL + o + LB128);
+        }
+        sync_ops();
+        TC_PROF(9);
+        // ===== gW1 = dz1 x (bar 0), overlapped with the Adam update of W2 =====
+        if (tid == 0) {
+            tcgen05_fence_after();
+            gemm2c(tmem + T_G1, sbase + S_DH, sbase + S_DL, 2 * LB128, LB128, 128,
+                   sbase + S_XH, 2 * 128, 128, LB64, NB / 16, ID_G1c, ID_G1);
+            mma_commit(&bars[0]);
+        }
+#pragma unroll
+        for (int c16 = 0; c16 < 2; ++c16) {                          // W2[u][32cq + 16 c16 ..]: moments in TMEM
+            uint32_t g[16], mm[16], vv[16];
+            tmem_ld16(tlane + T_G2 + 32 * cq + 16 * c16, g);
+            tmem_ld16(tlane + T_M + 32 * cq + 16 * c16, mm);
+            tmem_ld16(tlane + T_V + 32 * cq + 16 * c16, vv);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float mj = __uint_as_float(mm[j]), vj = __uint_as_float(vv[j]);
+                w2[16 * c16 + j] = adam_apply(__uint_as_float(g[j]) * (1.0f / (SG * SA)), w2[16 * c16 + j], mj, vj, ap);
+                mm[j] = __float_as_uint(mj); vv[j] = __float_as_uint(vj);
+            }
+            tmem_st16(tlane + T_M + 32 * cq + 16 * c16, mm);
+            tmem_st16(tlane + T_V + 32 * cq + 16 * c16, vv);
+#pragma unroll
+            for (int g8 = 0; g8 < 2; ++g8) {
+                float x[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = SW * w2[16 * c16 + 8 * g8 + j];
+                const uint32_t o = rowoff + (uint32_t)(4 * cq + 2 * c16 + g8) * LB128;
+                split8_store(x, smem + S_W2H + o, smem + S_W2L + o);
+            }
+        }
+        if (cq == 0) {                                               // b1, b2, w3 (fixed-order sums of the four partials)
+            const int gsrc[3] = {F_GB1, F_GB2, F_GW3};
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                const float g = ((sf[gsrc[p] + u] + sf[gsrc[p] + H + u]) + sf[gsrc[p] + 2 * H + u]) + sf[gsrc[p] + 3 * H + u];
+                float mj = sf[F_VEC + (3 * p + 1) * H + u], vj = sf[F_VEC + (3 * p + 2) * H + u];
+                sf[F_VEC + (3 * p + 0) * H + u] = adam_apply(g, sf[F_VEC + (3 * p + 0) * H + u], mj, vj, ap);
+                sf[F_VEC + (3 * p + 1) * H + u] = mj; sf[F_VEC + (3 * p + 2) * H + u] = vj;
+            }
+        }
+        if (tid == 0) {
+            const float g = ((sf[F_GB3] + sf[F_GB3 + 1]) + sf[F_GB3 + 2]) + sf[F_GB3 + 3];
+            float mj = sf[F_B3 + 1], vj = sf[F_B3 + 2];
+            sf[F_B3] = adam_apply(g, sf[F_B3], mj, vj, ap);
+            sf[F_B3 + 1] = mj; sf[F_B3 + 2] = vj;
+        }
+        TC_PROF(10);
+        wait0();                                                     // gW1 done (X and dz buffers free)
+        TC_PROF(11);
+        {                                                            // W1[u][8cq ..]: state in shared memory ([k][u])
+            uint32_t g[8], gl[8];
+            tmem_ld8(tlane + T_G1 + 8 * cq, g);
+            tmem_ld8(tlane + T_G1 + KP + 8 * cq, gl);
+            tmem_ld_wait();
+            float x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = 8 * cq + j;
+                float mj = sf[F_W1M + k * H + u], vj = sf[F_W1V + k * H + u];
+                const float wn = adam_apply((__uint_as_float(g[j]) + __uint_as_float(gl[j])) * (1.0f / (SG * SA)),
+                                            sf[F_W1W + k * H + u], mj, vj, ap);
+                sf[F_W1W + k * H + u] = wn; sf[F_W1M + k * H + u] = mj; sf[F_W1V + k * H + u] = vj;
+                x[j] = SW * wn;
+            }
+            const uint32_t o = rowoff + (uint32_t)cq * LB128;
+            split8_store(x, smem + S_W1H + o, smem + S_W1L + o);
+        }
+        if (s + 1 < a.steps) stage_x();                              // minibatch of step s+1
+        tmem_st_wait();
+        TC_PROF(12);
+    }
+    __syncthreads();
+    if (a.prof && tid < 16) a.prof[tid] += s_prof[tid];
+
+    // ---- write the state back (natural layout) ----
+    {
+        uint32_t mv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a.w[oW2 + u * H + 32 * cq + j] = w2[j];
+        tmem_ld32(tlane + T_M + 32 * cq, mv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a.m[oW2 + u * H + 32 * cq + j] = __uint_as_float(mv[j]);
+        tmem_ld32(tlane + T_V + 32 * cq, mv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a.v[oW2 + u * H + 32 * cq + j] = __uint_as_float(mv[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int k = 8 * cq + j;
+        if (k < K) {
+            a.w[oW1 + u * K + k] = sf[F_W1W + k * H + u];
+            a.m[oW1 + u * K + k] = sf[F_W1M + k * H + u];
+            a.v[oW1 + u * K + k] = sf[F_W1V + k * H + u];
+        }
+    }
+    if (cq == 0) {
+        const int offs[3] = {ob1, ob2, oW3};
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            a.w[offs[p] + u] = sf[F_VEC + (3 * p + 0) * H + u];
+            a.m[offs[p] + u] = sf[F_VEC + (3 * p + 1) * H + u];
+            a.v[offs[p] + u] = sf[F_VEC + (3 * p + 2) * H + u];
+        }
+    }
+    if (tid == 0) { a.w[ob3] = sf[F_B3]; a.m[ob3] = sf[F_B3 + 1]; a.v[ob3] = sf[F_B3 + 2]; }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, T_COLS);
+}
+
+__global__ void tc_adam_consts_kernel(float2* out, int steps, long long step0, float lr, float beta1, float beta2) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= steps) return;
+    const double t = (double)(step0 + s + 1);
+    const double bc1 = 1.0 - pow((double)beta1, t), bc2 = 1.0 - pow((double)beta2, t);
+    out[s] = make_float2((float)(1.0 / sqrt(bc2)), (float)(-((double)lr / bc1)));
+}
+
+long long* g_tc_prof = nullptr;
+
+}  // namespace
+
+void vf_tc_set_prof(long long* dev16) { g_tc_prof = dev16; }
+
+bool vf_tc_supported(int K, int H1, int H2, int batch) { return batch == NB && H1 == H && H2 == H && K >= 1 && K <= KP; }
+
+cudaError_t launch_vf_fit_tc(const VfFitArgs& v, const float* feat, const float* ret32, cudaStream_t s) {
+    static float2* consts = nullptr;
+    static int consts_cap = 0;
+    if (v.steps > consts_cap) {
+        if (consts) cudaFree(consts);
+        consts_cap = v.steps + 1024;
+        cudaError_t ce = cudaMalloc(&consts, sizeof(float2) * consts_cap);
+        if (ce != cudaSuccess) { consts = nullptr; consts_cap = 0; return ce; }
+    }
+    tc_adam_consts_kernel<<<(v.steps + 255) / 256, 256, 0, s>>>(consts, v.steps, v.step0, v.lr, v.beta1, v.beta2);
+    TcFitArgs a;
+    a.K = v.K; a.steps = v.steps; a.feat = feat; a.ret32 = ret32; a.perm = v.perm;
+    a.reg = v.reg; a.beta1 = v.beta1; a.beta2 = v.beta2; a.eps = v.eps;
+    a.w = v.w; a.m = v.m; a.v = v.v; a.consts = consts; a.prof = g_tc_prof;
+    cudaError_t e = cudaFuncSetAttribute(vf_fit_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S_TOTAL);
+    if (e != cudaSuccess) return e;
+    vf_fit_tc_kernel<<<1, NT, S_TOTAL, s>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace mjb

@@ -145,11 +145,11 @@ def test_policy_steps(case, cuda_device):
     eng.close()
 
 
-@pytest.mark.parametrize("cluster", [(16, True), (8, True), (8, False), (16, False), (0, False)])
+@pytest.mark.parametrize("cluster", [(1, True), (16, True), (8, True), (8, False), (16, False), (0, False)])
 @pytest.mark.parametrize("case", ["pm_5x50", "pm_40x25_ragged", "swim_40x250", "linear_30x200"])
 def test_baseline_fit(case, cluster, cuda_device):
     """cluster = (CTAs of the thread-block cluster running the sequential Adam chain, model-parallel?);
-    0 CTAs = single-CTA kernel.  linear_30x200 (44 input features) exercises the fallbacks of the cluster kernels."""
+    1 CTA = the single-SM tensor-core kernel (the default), 0 CTAs = single-CTA fp32-FMA kernel.  linear_30x200 (44 input features) exercises the fallbacks of the cluster kernels."""
     g = load_golden(case)
     paths = golden_paths(g)
     eng = make_engine(g, cuda_device)

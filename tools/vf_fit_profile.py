@@ -18,8 +18,11 @@ names_dp = ["fwd L1", "fwd L2", "out+dy", "W3 grad+delta2", "dgrad+wgrad W2", "w
             "cluster sync 2", "reload+commit"]
 names_mp = ["P1 L1 slice + E1 scatter", "wait h1 (E1)", "P2 L2 slice + E2", "wait y (E2)", "P3d gather issue (next step)",
             "wait dgrad (E3)", "P4 delta1 + P5 Adam + commit", "-", "P3a dy, small grads, delta2", "P3b dgrad + E3 scatter", "P3c wgrad W2"]
-for cl, mp in ((16, True), (8, True), (8, False), (16, False)):
-    names = names_mp if mp else names_dp
+names_tc = ["issue L1, gather loads", "wait L1", "E1 h1 + sync", "issue L2", "wait L2", "E2a h2, y partials + sync",
+            "E2b dy, dz2 + sync", "issue dh1 + gW2", "wait dh1", "E3 dz1 (+wait gW2) + sync", "issue gW1, Adam W2 + vectors",
+            "wait gW1", "Adam W1, stage X, st wait"]
+for cl, mp in ((1, True), (16, True), (8, True), (8, False), (16, False)):
+    names = names_tc if cl == 1 else (names_mp if mp else names_dp)
     eng.vf_set_state(w, np.zeros_like(w), np.zeros_like(w), 0)
     eng.vf_set_cluster(cl, mp)
     perm = rng.permutation(N).astype(np.int32)
@@ -31,9 +34,9 @@ for cl, mp in ((16, True), (8, True), (8, False), (16, False)):
     out = (C.c_longlong * 16)()
     eng.lib.mjb_dev_vf_profile(eng.h, out, 0)
     steps = N // 64 - 1
-    tot = sum(out[:11])
+    tot = sum(out[:13])
     print("cluster=%d model_parallel=%s: %.2f us/step wall, %d cycles/step" % (cl, mp, dt / steps * 1e6, tot // steps))
     for i, n in enumerate(names):
         if n == "-":
             continue
-        print("   %-16s %7d cyc  %5.1f%%" % (n, out[i] // steps, 100.0 * out[i] / tot))
+        print("   %-34s %7d cyc  %5.1f%%" % (n, out[i] // steps, 100.0 * out[i] / tot))
