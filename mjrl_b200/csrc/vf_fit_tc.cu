@@ -149,8 +149,9 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
     const uint32_t rowoff = (uint32_t)((u >> 3) * 128 + (u & 7) * 16);      // core-tiled row offset of unit u (rows = 128)
 
     // ---- load the state ----
+    const bool worker = true;
     float w2[32];                                                    // W2[u][32cq .. 32cq+31], fp32 master
-    {
+    if (worker) {
         uint32_t mv[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) w2[j] = a.w[oW2 + u * H + 32 * cq + j];
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
             split8_store(x, smem + S_W2H + o, smem + S_W2L + o);
         }
     }
-    {                                                                // W1[u][8cq .. 8cq+7] (zero beyond K)
+    if (worker) {                                                    // W1[u][8cq .. 8cq+7] (zero beyond K)
         float x[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
         const uint32_t o = rowoff + (uint32_t)cq * LB128;
         split8_store(x, smem + S_W1H + o, smem + S_W1L + o);
     }
-    if (cq == 0) {                                                   // vectors: b1, b2, w3 (w, m, v)
+    if (worker && cq == 0) {                                         // vectors: b1, b2, w3 (w, m, v)
         const int offs[3] = {ob1, ob2, oW3};
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
@@ -220,10 +221,12 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
         if (gk == 0) sf[F_T + gn] = tt;
     };
     int i1 = 0, i2 = 0;
-    load_rows(a.perm[gn]);
-    stage_x();
-    if (a.steps > 1) i1 = a.perm[NB + gn];
-    if (a.steps > 2) i2 = a.perm[2 * NB + gn];
+    if (worker) {
+        load_rows(a.perm[gn]);
+        stage_x();
+        if (a.steps > 1) i1 = a.perm[NB + gn];
+        if (a.steps > 2) i2 = a.perm[2 * NB + gn];
+    }
 
     const uint32_t ID_L1 = make_idesc_f16(128, NB, false, false);
     const uint32_t ID_L2 = make_idesc_f16(128, NB, false, true), ID_L2c = make_idesc_f16(128, 2 * NB, false, true);
@@ -243,8 +246,7 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
 
     for (int s = 0; s < a.steps; ++s) {
         sync_ops();                                                  // X(s), weights(s) staged
-        // ===== layer 1: z1^T = W1 x^T =====
-        if (tid == 0) {
+        if (tid == 0) {                                              // layer 1: z1^T = W1 x^T
             tcgen05_fence_after();
             gemm3(tmem + T_D, sbase + S_W1H, sbase + S_W1L, 2 * LB128, LB128, 128,
                   sbase + S_XH, sbase + S_XL, 2 * LB64, LB64, 128, KP / 16, ID_L1);
@@ -280,8 +282,7 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
         }
         sync_ops();
         TC_PROF(2);
-        // ===== layer 2: z2^T = W2 h1 =====
-        if (tid == 0) {
+        if (tid == 0) {                                              // layer 2: z2^T = W2 h1
             tcgen05_fence_after();
             gemm2c(tmem + T_D, sbase + S_W2H, sbase + S_W2L, 2 * LB128, LB128, 128,
                    sbase + S_HH, 2 * 128, 128, LB128, H / 16, ID_L2c, ID_L2);
@@ -364,19 +365,45 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
         }
         sync_ops();
         TC_PROF(6);
-        // ===== backward: dh1^T = W2^T dz2 (bar 0), gW2 = dz2 h1^T (bar 1) =====
-        if (tid == 0) {
+        if (tid == 0) {                                              // gW2 = dz2 h1^T -> bar 1, then dh1^T = W2^T dz2 -> bar 0
             tcgen05_fence_after();
-            gemm2c(tmem + T_D, sbase + S_W2H, sbase + S_W2L, 2 * 128, 128, LB128,
-                   sbase + S_DH, 2 * 128, 128, LB128, H / 16, ID_DHc, ID_DH);
-            mma_commit(&bars[0]);
             gemm3(tmem + T_G2, sbase + S_DH, sbase + S_DL, 2 * LB128, LB128, 128,
                   sbase + S_HH, sbase + S_HL, 2 * LB128, LB128, 128, NB / 16, ID_G2);
             mma_commit(&bars[1]);
+            gemm2c(tmem + T_D, sbase + S_W2H, sbase + S_W2L, 2 * 128, 128, LB128,
+                   sbase + S_DH, 2 * 128, 128, LB128, H / 16, ID_DHc, ID_DH);
+            mma_commit(&bars[0]);
         }
         TC_PROF(7);
-        wait0();
+        wait1();                                                     // gW2 done: its Adam half runs under the dh1 GEMM
+        auto adam_w2 = [&](int c16) {                                // W2[u][32cq + 16 c16 ..]: moments in TMEM
+            uint32_t g[16], mm[16], vv[16];
+            tmem_ld16(tlane + T_G2 + 32 * cq + 16 * c16, g);
+            tmem_ld16(tlane + T_M + 32 * cq + 16 * c16, mm);
+            tmem_ld16(tlane + T_V + 32 * cq + 16 * c16, vv);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float mj = __uint_as_float(mm[j]), vj = __uint_as_float(vv[j]);
+                w2[16 * c16 + j] = adam_apply(__uint_as_float(g[j]) * (1.0f / (SG * SA)), w2[16 * c16 + j], mj, vj, ap);
+                mm[j] = __float_as_uint(mj); vv[j] = __float_as_uint(vj);
+            }
+            tmem_st16(tlane + T_M + 32 * cq + 16 * c16, mm);
+            tmem_st16(tlane + T_V + 32 * cq + 16 * c16, vv);
+        };
+        auto store_w2 = [&](int c16) {                               // new operand rows (W2 must not be read by an MMA now)
+#pragma unroll
+            for (int g8 = 0; g8 < 2; ++g8) {
+                float x[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = SW * w2[16 * c16 + 8 * g8 + j];
+                const uint32_t o = rowoff + (uint32_t)(4 * cq + 2 * c16 + g8) * LB128;
+                split8_store(x, smem + S_W2H + o, smem + S_W2L + o);
+            }
+        };
+        adam_w2(0);
         TC_PROF(8);
+        wait0();                                                     // dh1 done: D ready, W2 and dz buffers free
         {                                                            // dz1 = relu'(z1) dh1 -> dz1^T operand rows
             uint32_t z[16], zl[16];
             tmem_ld16(tlane + T_D + 16 * cq, z);
@@ -394,44 +421,21 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) gb1 += x1[j];
             sf[F_GB1 + cq * H + u] = gb1 * (1.0f / SG);
-            wait1();                                                 // gW2 done: the dz buffer is free
             const uint32_t o = rowoff + (uint32_t)(2 * cq) * LB128;
             split8_store(x0, smem + S_DH + o, smem + S_DL + o);
             split8_store(x1, smem + S_DH + o + LB128, smem + S_DL + o + LB128);
         }
         sync_ops();
         TC_PROF(9);
-        // ===== gW1 = dz1 x (bar 0), overlapped with the Adam update of W2 =====
-        if (tid == 0) {
+        if (tid == 0) {                                              // gW1 = dz1 x -> bar 0, under the second Adam half of W2
             tcgen05_fence_after();
             gemm2c(tmem + T_G1, sbase + S_DH, sbase + S_DL, 2 * LB128, LB128, 128,
                    sbase + S_XH, 2 * 128, 128, LB64, NB / 16, ID_G1c, ID_G1);
             mma_commit(&bars[0]);
         }
-#pragma unroll
-        for (int c16 = 0; c16 < 2; ++c16) {                          // W2[u][32cq + 16 c16 ..]: moments in TMEM
-            uint32_t g[16], mm[16], vv[16];
-            tmem_ld16(tlane + T_G2 + 32 * cq + 16 * c16, g);
-            tmem_ld16(tlane + T_M + 32 * cq + 16 * c16, mm);
-            tmem_ld16(tlane + T_V + 32 * cq + 16 * c16, vv);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float mj = __uint_as_float(mm[j]), vj = __uint_as_float(vv[j]);
-                w2[16 * c16 + j] = adam_apply(__uint_as_float(g[j]) * (1.0f / (SG * SA)), w2[16 * c16 + j], mj, vj, ap);
-                mm[j] = __float_as_uint(mj); vv[j] = __float_as_uint(vj);
-            }
-            tmem_st16(tlane + T_M + 32 * cq + 16 * c16, mm);
-            tmem_st16(tlane + T_V + 32 * cq + 16 * c16, vv);
-#pragma unroll
-            for (int g8 = 0; g8 < 2; ++g8) {
-                float x[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) x[j] = SW * w2[16 * c16 + 8 * g8 + j];
-                const uint32_t o = rowoff + (uint32_t)(4 * cq + 2 * c16 + g8) * LB128;
-                split8_store(x, smem + S_W2H + o, smem + S_W2L + o);
-            }
-        }
+        store_w2(0);
+        adam_w2(1);
+        store_w2(1);
         if (cq == 0) {                                               // b1, b2, w3 (fixed-order sums of the four partials)
             const int gsrc[3] = {F_GB1, F_GB2, F_GW3};
 #pragma unroll
@@ -477,7 +481,7 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
     if (a.prof && tid < 16) a.prof[tid] += s_prof[tid];
 
     // ---- write the state back (natural layout) ----
-    {
+    if (worker) {
         uint32_t mv[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) a.w[oW2 + u * H + 32 * cq + j] = w2[j];
@@ -490,6 +494,7 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) a.v[oW2 + u * H + 32 * cq + j] = __uint_as_float(mv[j]);
     }
+    if (worker) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int k = 8 * cq + j;
@@ -499,7 +504,8 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
             a.v[oW1 + u * K + k] = sf[F_W1V + k * H + u];
         }
     }
-    if (cq == 0) {
+    }
+    if (worker && cq == 0) {
         const int offs[3] = {ob1, ob2, oW3};
 #pragma unroll
         for (int p = 0; p < 3; ++p) {

@@ -19,7 +19,7 @@ names_dp = ["fwd L1", "fwd L2", "out+dy", "W3 grad+delta2", "dgrad+wgrad W2", "w
 names_mp = ["P1 L1 slice + E1 scatter", "wait h1 (E1)", "P2 L2 slice + E2", "wait y (E2)", "P3d gather issue (next step)",
             "wait dgrad (E3)", "P4 delta1 + P5 Adam + commit", "-", "P3a dy, small grads, delta2", "P3b dgrad + E3 scatter", "P3c wgrad W2"]
 names_tc = ["issue L1, gather loads", "wait L1", "E1 h1 + sync", "issue L2", "wait L2", "E2a h2, y partials + sync",
-            "E2b dy, dz2 + sync", "issue dh1 + gW2", "wait dh1", "E3 dz1 (+wait gW2) + sync", "issue gW1, Adam W2 + vectors",
+            "E2b dy, dz2 + sync", "issue gW2 + dh1", "wait gW2, Adam W2 half 1", "wait dh1, E3 dz1 + sync", "issue gW1, Adam W2 half 2, vectors",
             "wait gW1", "Adam W1, stage X, st wait"]
 for cl, mp in ((1, True), (16, True), (8, True), (8, False), (16, False)):
     names = names_tc if cl == 1 else (names_mp if mp else names_dp)
