@@ -54,6 +54,7 @@ constexpr int SLF_SHIFT = 0, SLF_RINV = 384, SLF_C = 768, SLF_FAC = 800, SLF_END
 constexpr int SL_BAR = SL_F32 + SLF_END * 4;
 constexpr int SL_TOTAL = SL_BAR + 64;
 
+constexpr int FLUSH_TILES = 24;           // tiles per TMEM accumulation group (see flush() in the kernel)
 constexpr uint32_t TL_D1 = 0, TL_G = 64, TL_COLS = 256;   // TMEM columns: GEMM-1 output [0,64), G blocks 3 x 64
 
 struct LinTcArgs {
@@ -177,6 +178,37 @@ __global__ void __launch_bounds__(512, 1) linear_tc_kernel(const LinTcArgs a) {
         }
     };
 
+    // Adds the TMEM gradient accumulators to the per-CTA partial in global memory (zeroed before the launch, owned by this
+    // CTA): lane = feature, columns = action.  Called every FLUSH_TILES tiles because the tensor core's fp32 accumulation
+    // truncates -- an accumulator that lives for the whole kernel drifts by ~1.5e-7 (relative) per tile.
+    auto flush = [&]() {
+        float* gp = a.gpartial + (size_t)blockIdx.x * a.gstride;
+        if (warp < 4) {
+            const int kl = 32 * warp + lane;
+#pragma unroll 1
+            for (int j = 0; j < NFB; ++j) {
+                const int k = FB * j + kl;
+#pragma unroll 1
+                for (int c8 = 0; 8 * c8 < A; ++c8) {                     // 8 actions at a time: keeps the register footprint small
+                    uint32_t g0[8], g1[8];
+                    tmem_ld8(tmem + ((uint32_t)(32 * warp) << 16) + TL_G + DYC * j + 8 * c8, g0);
+                    tmem_ld8(tmem + ((uint32_t)(32 * warp) << 16) + TL_G + DYC * j + 32 + 8 * c8, g1);
+                    tmem_ld_wait();
+                    // red.global.add: fire-and-forget (no read round trip); the slice belongs to this CTA
+#pragma unroll
+                    for (int o8 = 0; o8 < 8; ++o8) {
+                        const int o = 8 * c8 + o8;
+                        const float gv = __uint_as_float(g0[o8]) + __uint_as_float(g1[o8]);
+                        if (o < A) {
+                            if (k < K0) atomicAdd(&gp[a.tW + o * K0 + k], gv);
+                            else if (k == K0) atomicAdd(&gp[a.tb + o], gv);
+                        }
+                    }
+                }
+            }
+        }
+        tcgen05_fence_before();
+    };
     const long long n_tiles = (a.n + LM - 1) / LM;
     const long long G = gridDim.x;
     long long it = 0;
@@ -186,6 +218,7 @@ __global__ void __launch_bounds__(512, 1) linear_tc_kernel(const LinTcArgs a) {
     if ((long long)blockIdx.x < n_tiles) issue_loads(blockIdx.x);
     for (long long tile = blockIdx.x; tile < n_tiles; tile += G, ++it) {
         const long long base = tile * LM;
+        const bool first = (it % FLUSH_TILES == 0);                  // first tile of an accumulation group
         stage();                                                     // consumes the prefetched registers
         LIN_PROF(0);
         fence_proxy_async();
@@ -259,40 +292,21 @@ __global__ void __launch_bounds__(512, 1) linear_tc_kernel(const LinTcArgs a) {
 #pragma unroll
                 for (int ks = 0; ks < XR / 16; ++ks)
                     mma_f16(tmem + TL_G + DYC * j, make_desc(xb + 2 * ks * 128, 128, X_LB),
-                            make_desc(sbase + SL_DY + 2 * ks * 128, 128, DY_LB), ID2, (it > 0) || ks > 0);
+                            make_desc(sbase + SL_DY + 2 * ks * 128, 128, DY_LB), ID2, !first || ks > 0);
             }
             mma_commit(&bars[0]);
         }
         LIN_PROF(4);
         all_wait_mma();                                              // the tile buffer is restaged next
         LIN_PROF(5);
+        if ((it + 1) % FLUSH_TILES == 0) flush();
     }
     if (a.prof && tid == 0) {
         for (int i = 0; i < 6; ++i) atomicAdd(a.prof + i, pacc[i]);
         atomicAdd(a.prof + 6, (unsigned long long)it);
     }
 
-    if (it > 0) {                                                    // write the per-CTA partial: lane = feature, cols = action
-        float* gp = a.gpartial + (size_t)blockIdx.x * a.gstride;
-        if (warp < 4) {
-            const int kl = 32 * warp + lane;
-            for (int j = 0; j < NFB; ++j) {
-                uint32_t g0[32], g1[32];
-                tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + TL_G + DYC * j, g0);
-                tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + TL_G + DYC * j + 32, g1);
-                tmem_ld_wait();
-                const int k = FB * j + kl;
-#pragma unroll
-                for (int o = 0; o < 32; ++o) {
-                    const float gv = __uint_as_float(g0[o]) + __uint_as_float(g1[o]);
-                    if (o < A) {
-                        if (k < K0) gp[a.tW + o * K0 + k] = gv;
-                        else if (k == K0) gp[a.tb + o] = gv;
-                    }
-                }
-            }
-        }
-    }
+    if (it > 0 && it % FLUSH_TILES != 0) flush();
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, TL_COLS);
