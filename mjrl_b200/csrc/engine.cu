@@ -111,6 +111,7 @@ struct mjb_engine {
     float* vf_feat = nullptr; float* vf_ret32 = nullptr; long long vf_feat_cap = 0;   // fp32 features / targets of the fit
     int vf_cluster = 1;       // fit kernel: 1 = single-SM tensor-core kernel, 8/16 = cluster kernels, 0 = single-CTA FMA kernel
     int vf_sms = 1;           // SMs the fit kernel in flight occupies (set at launch)
+    float2* vf_consts = nullptr; int vf_consts_cap = 0;   // per-step Adam constants of the fit kernels
     int vf_model_parallel = 1; // 1: hidden units split over the cluster (vf_fit_mp.cu); 0: minibatch rows split (vf_fit_cluster.cu)
     int* perm_dev = nullptr; long long perm_cap = 0;
     // global (all-rank) copies used by the replicated fit when world_size > 1
@@ -400,6 +401,7 @@ const char* mjb_last_error(const mjb_engine* e) { return e ? e->err.c_str() : g_
 void mjb_destroy(mjb_engine* e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
+    if (e->stream_vf) cudaStreamSynchronize(e->stream_vf);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->comm) g_nccl.CommDestroy(e->comm);
     void* bufs[] = {e->pnew.theta, e->pnew.prep, e->pnew.in_shift, e->pnew.in_scale, e->pnew.out_shift, e->pnew.out_scale,
@@ -407,7 +409,7 @@ void mjb_destroy(mjb_engine* e) {
                     e->prep_tan, e->tc_prep_new, e->tc_prep_tan, e->tc_vscale, e->obs, e->act, e->rew, e->path_off, e->term, e->tstep, e->ret, e->adv, e->base,
                     e->adv_white, e->weights, e->path_ret, e->ll_old, e->mu_old, e->gpartial, e->eval_partial,
                     e->mom_scratch, e->dsc, e->g, e->x, e->r, e->p, e->Fp, e->tmpv, e->idx_dev, e->stage64, e->vf_w,
-                    e->vf_m, e->vf_v, e->vf_wT, e->vf_prep, e->vf_cl_scratch, e->vf_feat, e->vf_ret32, e->perm_dev, e->fit_obs, e->fit_tstep, e->fit_ret};
+                    e->vf_m, e->vf_v, e->vf_wT, e->vf_prep, e->vf_cl_scratch, e->vf_feat, e->vf_ret32, e->vf_consts, e->perm_dev, e->fit_obs, e->fit_tstep, e->fit_ret};
     for (void* b : bufs) if (b) cudaFree(b);
     if (e->pinned) cudaFreeHost(e->pinned);
     if (e->h_dsc) cudaFreeHost(e->h_dsc);
@@ -1030,6 +1032,11 @@ static int vf_fit_launch(mjb_engine* e, const int32_t* perms, int epochs, int ba
         }
         if (vf_build_features(a, e->vf_feat, e->vf_ret32, e->stream) != cudaSuccess) FAIL(e, "vf feature kernel launch failed");
         e->launches += 1;
+        if (steps > e->vf_consts_cap) {
+            if (e->vf_consts) cudaFree(e->vf_consts);
+            e->vf_consts_cap = steps + 1024;
+            CK(e, cudaMalloc(&e->vf_consts, sizeof(float2) * (size_t)e->vf_consts_cap));
+        }
     }
     if (use_dp && !e->vf_cl_scratch)
         CK(e, cudaMalloc(&e->vf_cl_scratch, sizeof(float) * vf_cluster_scratch_floats(a.K, a.H1, a.H2, 16)));
@@ -1038,8 +1045,8 @@ static int vf_fit_launch(mjb_engine* e, const int32_t* perms, int epochs, int ba
         a.perm = e->perm_dev + (size_t)ep * N;
         a.step0 = e->vf_step;
         cudaError_t ce;
-        if (use_tc) { ce = launch_vf_fit_tc(a, e->vf_feat, e->vf_ret32, fs); e->launches += 2; }
-        else if (use_mp) { ce = launch_vf_fit_mp(a, e->vf_feat, e->vf_ret32, ccl, fs); e->launches += 2; }
+        if (use_tc) { ce = launch_vf_fit_tc(a, e->vf_feat, e->vf_ret32, e->vf_consts, fs); e->launches += 2; }
+        else if (use_mp) { ce = launch_vf_fit_mp(a, e->vf_feat, e->vf_ret32, e->vf_consts, ccl, fs); e->launches += 2; }
         else if (use_dp) { ce = launch_vf_fit_cluster(a, e->vf_cl_scratch, ccl, fs); e->launches += 3; }
         else { ce = launch_vf_fit(a, fs); e->launches += 1; }
         if (ce != cudaSuccess) FAIL(e, std::string("vf fit launch (batch<=64, multiple of 4; sizes must fit 220 KB smem): ") + cudaGetErrorString(ce));

@@ -124,11 +124,12 @@ cudaError_t launch_vf_fit_cluster(const VfFitArgs& a, float* scratch, int C, cud
 bool vf_mp_supported(int K, int H1, int H2, int batch, int C);
 void vf_mp_set_prof(long long* dev16);
 cudaError_t vf_build_features(const VfFitArgs& a, float* feat, float* ret32, cudaStream_t s);
-cudaError_t launch_vf_fit_mp(const VfFitArgs& a, const float* feat, const float* ret32, int C, cudaStream_t s);
+// consts: caller-owned scratch of >= a.steps float2 (per-step Adam bias-correction constants, filled by the launcher)
+cudaError_t launch_vf_fit_mp(const VfFitArgs& a, const float* feat, const float* ret32, float2* consts, int C, cudaStream_t s);
 // vf_fit_tc.cu : same chain on one SM with tcgen05 (units on the M axis, Adam moments of W2 in TMEM)
 bool vf_tc_supported(int K, int H1, int H2, int batch);
 void vf_tc_set_prof(long long* dev16);
-cudaError_t launch_vf_fit_tc(const VfFitArgs& a, const float* feat, const float* ret32, cudaStream_t s);
+cudaError_t launch_vf_fit_tc(const VfFitArgs& a, const float* feat, const float* ret32, float2* consts, cudaStream_t s);
 // err = sum((ret - pred)^2) / (sum(ret^2) + 1e-8) pieces: out = {sum err^2, sum ret^2} (fp32 casts like the reference)
 void launch_vf_error(const double* ret, const float* pred, long long n, double* scratch, double* out2, cudaStream_t s);
 

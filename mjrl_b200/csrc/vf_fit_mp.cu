@@ -487,15 +487,7 @@ cudaError_t vf_build_features(const VfFitArgs& v, float* feat, float* ret32, cud
     return cudaGetLastError();
 }
 
-cudaError_t launch_vf_fit_mp(const VfFitArgs& v, const float* feat, const float* ret32, int C, cudaStream_t s) {
-    static float2* consts = nullptr;
-    static int consts_cap = 0;
-    if (v.steps > consts_cap) {
-        if (consts) cudaFree(consts);
-        consts_cap = v.steps + 1024;
-        cudaError_t ce = cudaMalloc(&consts, sizeof(float2) * consts_cap);
-        if (ce != cudaSuccess) { consts = nullptr; consts_cap = 0; return ce; }
-    }
+cudaError_t launch_vf_fit_mp(const VfFitArgs& v, const float* feat, const float* ret32, float2* consts, int C, cudaStream_t s) {
     mp_adam_consts_kernel<<<(v.steps + 255) / 256, 256, 0, s>>>(consts, v.steps, v.step0, v.lr, v.beta1, v.beta2);
     MpArgs a;
     a.K = v.K; a.H1 = v.H1; a.H2 = v.H2; a.u1 = v.H1 / C; a.u2 = v.H2 / C; a.obs_dim = v.obs_dim; a.steps = v.steps;

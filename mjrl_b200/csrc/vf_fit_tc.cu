@@ -536,15 +536,7 @@ void vf_tc_set_prof(long long* dev16) { g_tc_prof = dev16; }
 
 bool vf_tc_supported(int K, int H1, int H2, int batch) { return batch == NB && H1 == H && H2 == H && K >= 1 && K <= KP; }
 
-cudaError_t launch_vf_fit_tc(const VfFitArgs& v, const float* feat, const float* ret32, cudaStream_t s) {
-    static float2* consts = nullptr;
-    static int consts_cap = 0;
-    if (v.steps > consts_cap) {
-        if (consts) cudaFree(consts);
-        consts_cap = v.steps + 1024;
-        cudaError_t ce = cudaMalloc(&consts, sizeof(float2) * consts_cap);
-        if (ce != cudaSuccess) { consts = nullptr; consts_cap = 0; return ce; }
-    }
+cudaError_t launch_vf_fit_tc(const VfFitArgs& v, const float* feat, const float* ret32, float2* consts, cudaStream_t s) {
     tc_adam_consts_kernel<<<(v.steps + 255) / 256, 256, 0, s>>>(consts, v.steps, v.step0, v.lr, v.beta1, v.beta2);
     TcFitArgs a;
     a.K = v.K; a.steps = v.steps; a.feat = feat; a.ret32 = ret32; a.perm = v.perm;
