@@ -171,6 +171,14 @@ int  mjb_vf_fit_end(mjb_engine* e, double* err_after);
  * cluster_ctas 0 = single-CTA fp32-FMA kernel (also the last fallback for shapes no other kernel covers). */
 int  mjb_vf_set_cluster(mjb_engine* e, int cluster_ctas, int model_parallel);
 
+/* ---- host helper ---------------------------------------------------------------------------- */
+/* np.random.permutation(n) of numpy's global legacy RandomState, bit for bit: the minibatch order MLPBaseline.fit
+ * draws per epoch (utils/optimize_model.py:22).  mt_key624 / mt_pos are numpy's MT19937 state
+ * (np.random.get_state()[1:3]); they are advanced in place exactly as numpy would, so the caller writes them back
+ * with np.random.set_state and every later draw of the program is unchanged.  Pure host code (no device needed);
+ * 2-3x faster than numpy's element-wise loop, which sits on the critical path of the fit.  out: n int32. */
+int  mjb_host_permutation(uint32_t* mt_key624, int32_t* mt_pos, int64_t n, int32_t* out);
+
 /* ---- introspection for benchmarks ------------------------------------------------------------ */
 /* CUDA events on the engine's stream (slots 0..7) so callers time on the device, not by wall clock. */
 int  mjb_event_record(mjb_engine* e, int slot);

@@ -82,6 +82,7 @@ _SIGNATURES = {
     "mjb_event_record": (C.c_int, [_P, C.c_int]),
     "mjb_event_elapsed_ms": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "mjb_kernel_launches": (C.c_int64, [_P]),
+    "mjb_host_permutation": (C.c_int, [_P, C.POINTER(C.c_int32), C.c_int64, _P]),
     "mjb_fvp_timing": (C.c_int, [_P, C.POINTER(C.c_float)]),
 }
 

@@ -110,10 +110,9 @@ class MLPBaseline:
             eng.set_returns(np.concatenate([p["returns"] for p in paths]))
             eng.have_returns = True
         n_glob = eng.n_global()
-        # host RNG draw at the reference's program point (optimize_model.py:22): one permutation per epoch
-        # (permuting an int32 arange consumes the global RNG exactly like np.random.permutation(n) and yields the same
-        # order, without the int64 temporary -- 3-4x faster on the host critical path)
-        perms = np.stack([np.random.permutation(np.arange(n_glob, dtype=np.int32)) for _ in range(self.epochs)])
+        # host RNG draw at the reference's program point (optimize_model.py:22): one permutation per epoch, from
+        # numpy's global RandomState (bit-identical order and RNG state, see runtime.global_permutation)
+        perms = np.stack([runtime.global_permutation(n_glob) for _ in range(self.epochs)])
         return eng.vf_fit_begin(perms, self.batch_size, self.learn_rate, self.reg_coef, return_errors=return_errors)
 
     def fit_end(self, return_errors=False):

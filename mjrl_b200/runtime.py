@@ -4,6 +4,8 @@ The reference has no such object -- its policy, baseline and agent talk through 
 Here they share one device-resident engine so a rollout batch is uploaded once per train_step."""
 import os
 
+import numpy as np
+
 from mjrl_b200.engine import Engine
 
 _engines = {}
@@ -55,6 +57,25 @@ def get_engine(obs_dim, act_dim, hidden=None, vf_hidden=(128, 128), min_log_std=
             eng.vf_set_state(w, m, v, step)
         _engines[key] = eng
     return eng
+
+
+def global_permutation(n):
+    """np.random.permutation(n) as int32, drawn from numpy's GLOBAL RandomState at this program point
+    (optimize_model.py:22) -- same order, same RNG state afterwards -- through the library's batched MT19937 /
+    Fisher-Yates loops (`mjb_host_permutation`), which are 2-3x faster than numpy's element-wise loop."""
+    import ctypes as C
+    from mjrl_b200 import _native
+    st = np.random.get_state()
+    if st[0] != "MT19937" or n < 2 or n > 0x7fffffff:
+        return np.random.permutation(np.arange(n, dtype=np.int32))
+    key = np.array(st[1], dtype=np.uint32, copy=True, order="C")
+    pos = C.c_int32(int(st[2]))
+    out = np.empty(n, dtype=np.int32)
+    rc = _native.load().mjb_host_permutation(key.ctypes.data_as(C.c_void_p), C.byref(pos), int(n), out.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise RuntimeError("mjb_host_permutation failed (%d)" % rc)
+    np.random.set_state(("MT19937", key, int(pos.value), st[3], st[4]))
+    return out
 
 
 def fingerprint(paths):

@@ -76,3 +76,29 @@ def test_host_classes_construct_on_cpu():
         assert a.FIM_invert_args == {'iters': 10, 'damping': 1e-4}
     A = np.array([[4.0, 1.0], [1.0, 3.0]])
     assert np.allclose(cg_solve(lambda v: A.dot(v), np.array([1.0, 2.0]), cg_iters=2), [1 / 11, 7 / 11])
+
+
+def test_host_permutation_is_numpys():
+    """mjb_host_permutation reproduces np.random.permutation(n) of the global RandomState bit for bit -- the order
+    AND the generator state afterwards (MLPBaseline.fit's minibatch order, optimize_model.py:22)."""
+    import numpy as np
+    from mjrl_b200 import runtime
+    for seed, n in [(0, 2), (1, 3), (2, 64), (3, 1000), (4, 4096), (5, 4097), (123, 65536), (7, 250000), (8, 1000003)]:
+        np.random.seed(seed)
+        np.random.rand(seed % 5)                          # start from an arbitrary position inside the MT block
+        want = np.random.permutation(n)
+        after_want = np.random.randint(0, 1 << 30, size=5)
+        np.random.seed(seed)
+        np.random.rand(seed % 5)
+        got = runtime.global_permutation(n)
+        after_got = np.random.randint(0, 1 << 30, size=5)
+        assert got.dtype == np.int32 and np.array_equal(got, want), (seed, n)
+        assert np.array_equal(after_got, after_want), (seed, n)
+    # a gaussian cached in the state (has_gauss) survives the round trip
+    np.random.seed(11)
+    np.random.randn(3)
+    a = np.random.permutation(1000); x = np.random.randn()
+    np.random.seed(11)
+    np.random.randn(3)
+    b = runtime.global_permutation(1000); y = np.random.randn()
+    assert np.array_equal(a, b) and x == y
