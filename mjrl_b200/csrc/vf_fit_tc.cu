@@ -14,8 +14,11 @@
 // All operands are two-term fp16 splits (hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM), written by the epilogue
 // threads in the no-swizzle core-tiled layout of tc_common.cuh: thread (unit u, column quarter) owns a TMEM lane, so
 // it writes whole 16-byte core-matrix rows and nothing is ever transposed.
+// The B operand's two terms are N-concatenated ([B hi | B lo] are adjacent column groups), so a product costs two
+// MMAs per k-step; small operands carry power-of-two scales (SW, SA, SG below) that keep their fp16 low terms normal.
 // State: W2's fp32 master copy lives in registers (32 per thread), its Adam moments in TMEM (2 x 128 columns), W1's
-// state and the small vectors in shared memory.  512 threads; thread 0 issues the MMAs.
+// state and the small vectors in shared memory.  512 threads; thread 0 issues the MMAs; gW2 is issued before dh1 so
+// that half of W2's Adam update runs under the dh1 GEMM.
 // Semantics (minibatch order, 1/B scaling, L2-in-gradient weight decay, bias correction, state persistence) are the
 // reference's; sums run in a fixed order (deterministic).
 #include <cuda_fp16.h>
@@ -81,12 +84,6 @@ __device__ __forceinline__ float adam_apply(float g, float w, float& m, float& v
     return fmaf(c.neg_step, m * rc, w);
 }
 
-
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n"
-                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
-}
-
 // 8 consecutive fp32 values -> fp16 hi / lo, one 16-byte core-matrix row each
 __device__ __forceinline__ void split8_store(const float (&x)[8], unsigned char* hi, unsigned char* lo) {
     __half2 h[4], l[4];
@@ -149,9 +146,8 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
     const uint32_t rowoff = (uint32_t)((u >> 3) * 128 + (u & 7) * 16);      // core-tiled row offset of unit u (rows = 128)
 
     // ---- load the state ----
-    const bool worker = true;
     float w2[32];                                                    // W2[u][32cq .. 32cq+31], fp32 master
-    if (worker) {
+    {
         uint32_t mv[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) w2[j] = a.w[oW2 + u * H + 32 * cq + j];
@@ -171,7 +167,7 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
             split8_store(x, smem + S_W2H + o, smem + S_W2L + o);
         }
     }
-    if (worker) {                                                    // W1[u][8cq .. 8cq+7] (zero beyond K)
+    {                                                                // W1[u][8cq .. 8cq+7] (zero beyond K)
         float x[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -186,7 +182,7 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
         const uint32_t o = rowoff + (uint32_t)cq * LB128;
         split8_store(x, smem + S_W1H + o, smem + S_W1L + o);
     }
-    if (worker && cq == 0) {                                         // vectors: b1, b2, w3 (w, m, v)
+    if (cq == 0) {                                                   // vectors: b1, b2, w3 (w, m, v)
         const int offs[3] = {ob1, ob2, oW3};
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
@@ -221,12 +217,10 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
         if (gk == 0) sf[F_T + gn] = tt;
     };
     int i1 = 0, i2 = 0;
-    if (worker) {
-        load_rows(a.perm[gn]);
-        stage_x();
-        if (a.steps > 1) i1 = a.perm[NB + gn];
-        if (a.steps > 2) i2 = a.perm[2 * NB + gn];
-    }
+    load_rows(a.perm[gn]);
+    stage_x();
+    if (a.steps > 1) i1 = a.perm[NB + gn];
+    if (a.steps > 2) i2 = a.perm[2 * NB + gn];
 
     const uint32_t ID_L1 = make_idesc_f16(128, NB, false, false);
     const uint32_t ID_L2 = make_idesc_f16(128, NB, false, true), ID_L2c = make_idesc_f16(128, 2 * NB, false, true);
@@ -481,7 +475,7 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
     if (a.prof && tid < 16) a.prof[tid] += s_prof[tid];
 
     // ---- write the state back (natural layout) ----
-    if (worker) {
+    {
         uint32_t mv[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) a.w[oW2 + u * H + 32 * cq + j] = w2[j];
@@ -494,7 +488,6 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) a.v[oW2 + u * H + 32 * cq + j] = __uint_as_float(mv[j]);
     }
-    if (worker) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int k = 8 * cq + j;
@@ -504,8 +497,7 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
             a.v[oW1 + u * K + k] = sf[F_W1V + k * H + u];
         }
     }
-    }
-    if (worker && cq == 0) {
+    if (cq == 0) {
         const int offs[3] = {ob1, ob2, oW3};
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
