@@ -320,7 +320,8 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
             p[0] += __shfl_xor_sync(0xffffffffu, p[0], 1);
             if ((lane & 1) == 0) sf[F_YP + q * NB + 16 * cq + (lane >> 1)] = p[0];
         }
-        __syncthreads();
+        // the 16 outputs of this column quarter need the partials of its four warps only: named barrier 1 + cq
+        asm volatile("bar.sync %0, 128;\n" ::"r"(1 + cq) : "memory");
         TC_PROF(5);
         {                                                            // dy, small gradients, dz2^T operand rows
             const float b3 = sf[F_B3];
@@ -430,17 +431,15 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
         store_w2(0);
         adam_w2(1);
         store_w2(1);
-        if (cq == 0) {                                               // b1, b2, w3 (fixed-order sums of the four partials)
-            const int gsrc[3] = {F_GB1, F_GB2, F_GW3};
-#pragma unroll
-            for (int p = 0; p < 3; ++p) {
-                const float g = ((sf[gsrc[p] + u] + sf[gsrc[p] + H + u]) + sf[gsrc[p] + 2 * H + u]) + sf[gsrc[p] + 3 * H + u];
-                float mj = sf[F_VEC + (3 * p + 1) * H + u], vj = sf[F_VEC + (3 * p + 2) * H + u];
-                sf[F_VEC + (3 * p + 0) * H + u] = adam_apply(g, sf[F_VEC + (3 * p + 0) * H + u], mj, vj, ap);
-                sf[F_VEC + (3 * p + 1) * H + u] = mj; sf[F_VEC + (3 * p + 2) * H + u] = vj;
-            }
+        if (cq >= 1) {                                               // b1, b2, w3: one vector per column quarter 1..3 (the issuer's
+            const int p = cq - 1;                                    // quarter 0 stays light); fixed-order sums of the four partials
+            const int gsrc = p == 0 ? F_GB1 : (p == 1 ? F_GB2 : F_GW3);
+            const float g = ((sf[gsrc + u] + sf[gsrc + H + u]) + sf[gsrc + 2 * H + u]) + sf[gsrc + 3 * H + u];
+            float mj = sf[F_VEC + (3 * p + 1) * H + u], vj = sf[F_VEC + (3 * p + 2) * H + u];
+            sf[F_VEC + (3 * p + 0) * H + u] = adam_apply(g, sf[F_VEC + (3 * p + 0) * H + u], mj, vj, ap);
+            sf[F_VEC + (3 * p + 1) * H + u] = mj; sf[F_VEC + (3 * p + 2) * H + u] = vj;
         }
-        if (tid == 0) {
+        if (tid == NT - 1) {
             const float g = ((sf[F_GB3] + sf[F_GB3 + 1]) + sf[F_GB3 + 2]) + sf[F_GB3 + 3];
             float mj = sf[F_B3 + 1], vj = sf[F_B3 + 2];
             sf[F_B3] = adam_apply(g, sf[F_B3], mj, vj, ap);
