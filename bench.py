@@ -270,11 +270,11 @@ def run_gpu(args, cfg, rank, world, local_rank):
 
     def device_step():
         eng.compute_returns(GAMMA)
-        eng.vf_predict()
-        eng.compute_advantages(GAMMA, LAM)
         # host RNG draw, as optimize_model.py:22 (same order and RNG state as np.random.permutation(n), batched loops)
         perm = runtime.global_permutation(n_glob)
         eng.vf_fit_begin(perm, VF["batch_size"], VF["learn_rate"], VF["reg_coef"])   # side stream: needs only the returns
+        eng.vf_predict(prefit=True)           # pre-fit baseline, as in the reference's program order
+        eng.compute_advantages(GAMMA, LAM)
         eng.process_paths()
         st = eng.step(cfg["algo"], **step_args)
         eng.vf_fit_end()

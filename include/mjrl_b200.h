@@ -102,6 +102,10 @@ int64_t mjb_batch_size(const mjb_engine* e, int which);
 /* ---- returns / advantages (utils/process_samples.py:3-35) ----------------------------------- */
 int  mjb_compute_returns(mjb_engine* e, double gamma);                 /* compute_returns :3-5        */
 int  mjb_vf_predict(mjb_engine* e);                                    /* MLPBaseline.predict, all paths (baselines/mlp_baseline.py:97-105) */
+/* Same, evaluated with the baseline as of the last COMPLETED fit and without joining a fit in flight: the reference
+ * computes the advantages with the pre-fit baseline (batch_reinforce.py:98 runs before :108), so the agents may start
+ * this step's fit (mjb_vf_fit_begin) first and call this afterwards. */
+int  mjb_vf_predict_prefit(mjb_engine* e);
 int  mjb_compute_advantages(mjb_engine* e, double gamma, double gae_lambda, int use_gae); /* :7-35    */
 int  mjb_get_returns(mjb_engine* e, double* out);                      /* host-or-device, N doubles   */
 int  mjb_get_baseline(mjb_engine* e, float* out);                      /* N floats                    */

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "mjb_batch_size": (C.c_int64, [_P, C.c_int]),
     "mjb_compute_returns": (C.c_int, [_P, C.c_double]),
     "mjb_vf_predict": (C.c_int, [_P]),
+    "mjb_vf_predict_prefit": (C.c_int, [_P]),
     "mjb_compute_advantages": (C.c_int, [_P, C.c_double, C.c_double, C.c_int]),
     "mjb_get_returns": (C.c_int, [_P, _P]),
     "mjb_get_baseline": (C.c_int, [_P, _P]),

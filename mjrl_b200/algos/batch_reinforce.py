@@ -125,18 +125,21 @@ class BatchREINFORCE:
     def update_from_paths(self, paths, gamma=0.995, gae_lambda=0.97):
         """Everything train_step does after sampling (batch_reinforce.py:94-112) on one resident device batch."""
         eng = self._resident(paths)
-        process_samples.returns_on(eng, paths, gamma)
-        process_samples.advantages_on(eng, paths, self.baseline, gamma, gae_lambda)
         overlap = hasattr(self.baseline, "fit_begin")
+        process_samples.returns_on(eng, paths, gamma, write_back=not overlap)
         ts = timer.time()
         if overlap:
-            # The sequential baseline fit depends only on the returns: start it now on the engine's side stream so it
-            # runs concurrently with the policy update.  Host RNG draws keep the reference's order (A9): the FVP
-            # subsample indices of this step first, then the fit permutations.
+            # The sequential baseline fit is the longest chain of the step and depends only on the returns: start it
+            # right away on the engine's side stream; the write-back of the returns, the advantages (with the PRE-fit
+            # baseline, as in the reference's program order) and the policy update run concurrently.  Host RNG draws
+            # keep the reference's order (A9): the FVP subsample indices of this step first, then the fit permutations.
             self._pending_hvp_idx = self._draw_hvp_indices(eng.n, self.FIM_invert_args['iters']) \
                 if hasattr(self, "_draw_hvp_indices") else None
             self._hvp_idx_drawn = True
+            self.baseline._bind(eng)
             error_before = self.baseline.fit_begin(paths, return_errors=self.save_logs)
+            process_samples.returns_write_back(eng, paths)
+        process_samples.advantages_on(eng, paths, self.baseline, gamma, gae_lambda, fit_in_flight=overlap)
         eval_statistics = self.train_from_paths(paths)
         if self.save_logs:
             self.logger.log_kv('num_samples', int(np.sum([p["rewards"].shape[0] for p in paths])))

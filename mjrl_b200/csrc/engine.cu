@@ -672,15 +672,26 @@ int mjb_compute_returns(mjb_engine* e, double gamma) {
 
 int mjb_vf_fit_end(mjb_engine* e, double* err_after);
 
+static int vf_predict_impl(mjb_engine* e);
+
 int mjb_vf_predict(mjb_engine* e) {
     if (e->fit_in_flight && mjb_vf_fit_end(e, nullptr)) return -1;
+    return vf_predict_impl(e);
+}
+
+// Predictions with the weights of the last COMPLETED fit, without joining a fit in flight: the kernel reads the prepared
+// copy (vf_prep) that only mjb_vf_fit_end / mjb_vf_set_state refresh, never the live weights the fit is updating.
+int mjb_vf_predict_prefit(mjb_engine* e) { return vf_predict_impl(e); }
+
+static int vf_predict_impl(mjb_engine* e) {
     if (e->occ[MODE_VF] == 0) {
         e->occ[MODE_VF] = occupancy_any(e->vfH, MODE_VF, e->VPL.YR);
         if (e->occ[MODE_VF] <= 0) FAIL(e, "vf kernel does not fit");
     }
     const int MT = mlp_tile_rows_for(e->vfH);
     const long long tiles = (e->n_roll + MT - 1) / MT;
-    const int grid = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)e->occ[MODE_VF] * e->num_sms));
+    const int sms = e->num_sms - (e->fit_in_flight ? e->vf_sms : 0);
+    const int grid = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)e->occ[MODE_VF] * sms));
     MlpArgs a;
     memset(&a, 0, sizeof(a));
     a.L = e->VPL; a.P = e->vf_prep; a.obs = e->obs; a.obs_dim = e->cfg.obs_dim; a.tstep = e->tstep; a.n = e->n_roll;

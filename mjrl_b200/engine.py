@@ -145,8 +145,12 @@ class Engine:
     def compute_returns(self, gamma):
         self._ck(self.lib.mjb_compute_returns(self.h, float(gamma)), "compute_returns")
 
-    def vf_predict(self):
-        self._ck(self.lib.mjb_vf_predict(self.h), "vf_predict")
+    def vf_predict(self, prefit=False):
+        """prefit=True: predictions with the baseline of the last completed fit, without joining a fit in flight."""
+        if prefit:
+            self._ck(self.lib.mjb_vf_predict_prefit(self.h), "vf_predict_prefit")
+        else:
+            self._ck(self.lib.mjb_vf_predict(self.h), "vf_predict")
 
     def compute_advantages(self, gamma, gae_lambda):
         use_gae = gae_lambda is not None and 0.0 <= gae_lambda <= 1.0

@@ -31,10 +31,15 @@ def compute_returns(paths, gamma):
     returns_on(_engine_for(paths), paths, gamma)
 
 
-def returns_on(eng, paths, gamma):
+def returns_on(eng, paths, gamma, write_back=True):
     runtime.ensure_resident(eng, paths)
     eng.compute_returns(gamma)
     eng.have_returns = True
+    if write_back:
+        _scatter(paths, "returns", eng.returns())
+
+
+def returns_write_back(eng, paths):
     _scatter(paths, "returns", eng.returns())
 
 
@@ -44,7 +49,9 @@ def compute_advantages(paths, baseline, gamma, gae_lambda=None, normalize=False)
     advantages_on(_engine_for(paths, baseline), paths, baseline, gamma, gae_lambda, normalize)
 
 
-def advantages_on(eng, paths, baseline, gamma, gae_lambda=None, normalize=False):
+def advantages_on(eng, paths, baseline, gamma, gae_lambda=None, normalize=False, fit_in_flight=False):
+    """fit_in_flight: this step's baseline fit was already launched (it only needs the returns); the advantages use the
+    pre-fit baseline exactly as the reference's program order does (batch_reinforce.py:98 before :108)."""
     runtime.ensure_resident(eng, paths)
     if not getattr(eng, "have_returns", False):
         if "returns" in paths[0]:
@@ -53,9 +60,10 @@ def advantages_on(eng, paths, baseline, gamma, gae_lambda=None, normalize=False)
             eng.compute_returns(gamma)
         eng.have_returns = True
     if hasattr(baseline, "_eng"):
-        baseline._bind(eng)
-        baseline._eng()                                # push the host weights if they changed
-        eng.vf_predict()                               # all paths in one launch (mlp_baseline.py:97-105)
+        if not fit_in_flight:
+            baseline._bind(eng)
+            baseline._eng()                            # push the host weights if they changed
+        eng.vf_predict(prefit=fit_in_flight)           # all paths in one launch (mlp_baseline.py:97-105)
         base = eng.baseline()
     else:                                              # any other baseline object keeps working on the host
         base = np.concatenate([np.asarray(baseline.predict(p), dtype=np.float32).ravel() for p in paths])
