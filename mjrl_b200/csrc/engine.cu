@@ -654,6 +654,7 @@ int mjb_batch_set_baseline(mjb_engine* e, const float* base_concat) {
 }
 
 int mjb_batch_set_returns(mjb_engine* e, const double* ret_concat) {
+    if (e->fit_in_flight && mjb_vf_fit_end(e, nullptr)) return -1;       // the fallback fit kernels read the returns in place
     CK(e, cudaMemcpyAsync(e->ret, ret_concat, sizeof(double) * e->n_roll, cudaMemcpyDefault, e->stream));
     return 0;
 }
@@ -664,6 +665,7 @@ int64_t mjb_batch_size(const mjb_engine* e, int which) {
 
 // ------------------------------------------------------------------------------- returns / advantages
 int mjb_compute_returns(mjb_engine* e, double gamma) {
+    if (e->fit_in_flight && mjb_vf_fit_end(e, nullptr)) return -1;       // the fallback fit kernels read the returns in place
     launch_returns(e->rew, e->path_off, e->n_paths, gamma, e->ret, e->stream);
     e->launches += 1;
     CK(e, cudaGetLastError());

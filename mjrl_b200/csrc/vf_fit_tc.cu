@@ -84,6 +84,38 @@ __device__ __forceinline__ float adam_apply(float g, float w, float& m, float& v
     return fmaf(c.neg_step, m * rc, w);
 }
 
+// ---- packed fp32x2 arithmetic (sm_100 FFMA2 / FMUL2 / FADD2): two IEEE-rounded lanes per instruction, bit-identical to
+//      the scalar forms; halves the issue slots of the element-wise Adam update ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(f32x2 r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+struct AdamP2 { f32x2 one_m_b1, b2, one_m_b2, rbc2_sqrt, eps, neg_step, reg, gscale; };
+
+// two parameters at once; same operation sequence as adam_apply (so the results are bit-identical)
+__device__ __forceinline__ void adam_apply2(float g0, float g1, float& w0, float& w1, float& m0, float& m1, float& v0, float& v1,
+                                            const AdamP2& c) {
+    const f32x2 w = pk2(w0, w1);
+    f32x2 m = pk2(m0, m1), v = pk2(v0, v1);
+    f32x2 g = mul2(pk2(g0, g1), c.gscale);
+    g = fma2(c.reg, w, g);
+    m = fma2(c.one_m_b1, sub2(g, m), m);
+    v = fma2(mul2(c.one_m_b2, g), g, mul2(v, c.b2));
+    upk2(v, v0, v1);
+    float s0, s1, r0, r1;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s0) : "f"(v0));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s1) : "f"(v1));
+    float d0, d1;
+    upk2(fma2(pk2(s0, s1), c.rbc2_sqrt, c.eps), d0, d1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
+    upk2(fma2(c.neg_step, mul2(m, pk2(r0, r1)), w), w0, w1);
+    upk2(m, m0, m1);
+}
+
 // 8 consecutive fp32 values -> fp16 hi / lo, one 16-byte core-matrix row each
 __device__ __forceinline__ void split8_store(const float (&x)[8], unsigned char* hi, unsigned char* lo) {
     __half2 h[4], l[4];
@@ -237,6 +269,10 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
 
     AdamP ap;
     ap.one_m_b1 = 1.0f - a.beta1; ap.b2 = a.beta2; ap.one_m_b2 = 1.0f - a.beta2; ap.eps = a.eps; ap.reg = a.reg;
+    AdamP2 ap2;
+    ap2.one_m_b1 = pk2(ap.one_m_b1, ap.one_m_b1); ap2.b2 = pk2(ap.b2, ap.b2); ap2.one_m_b2 = pk2(ap.one_m_b2, ap.one_m_b2);
+    ap2.eps = pk2(ap.eps, ap.eps); ap2.reg = pk2(ap.reg, ap.reg); ap2.gscale = pk2(1.0f / (SG * SA), 1.0f / (SG * SA));
+    ap2.rbc2_sqrt = ap2.neg_step = 0;
 
     for (int s = 0; s < a.steps; ++s) {
         sync_ops();                                                  // X(s), weights(s) staged
@@ -251,6 +287,7 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
         if (s + 3 < a.steps) i2 = a.perm[(size_t)(s + 3) * NB + gn];
         const float2 cst = a.consts[s];
         ap.rbc2_sqrt = cst.x; ap.neg_step = cst.y;
+        ap2.rbc2_sqrt = pk2(cst.x, cst.x); ap2.neg_step = pk2(cst.y, cst.y);
         TC_PROF(0);
         wait0();
         TC_PROF(1);
@@ -378,10 +415,12 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
             tmem_ld16(tlane + T_V + 32 * cq + 16 * c16, vv);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float mj = __uint_as_float(mm[j]), vj = __uint_as_float(vv[j]);
-                w2[16 * c16 + j] = adam_apply(__uint_as_float(g[j]) * (1.0f / (SG * SA)), w2[16 * c16 + j], mj, vj, ap);
-                mm[j] = __float_as_uint(mj); vv[j] = __float_as_uint(vj);
+            for (int j = 0; j < 16; j += 2) {
+                float m0 = __uint_as_float(mm[j]), m1 = __uint_as_float(mm[j + 1]);
+                float v0 = __uint_as_float(vv[j]), v1 = __uint_as_float(vv[j + 1]);
+                adam_apply2(__uint_as_float(g[j]), __uint_as_float(g[j + 1]), w2[16 * c16 + j], w2[16 * c16 + j + 1], m0, m1, v0, v1, ap2);
+                mm[j] = __float_as_uint(m0); mm[j + 1] = __float_as_uint(m1);
+                vv[j] = __float_as_uint(v0); vv[j + 1] = __float_as_uint(v1);
             }
             tmem_st16(tlane + T_M + 32 * cq + 16 * c16, mm);
             tmem_st16(tlane + T_V + 32 * cq + 16 * c16, vv);
