@@ -2,8 +2,12 @@
 baseline.  Environments / MuJoCo stepping stay on the host in mjrl itself (out of scope)."""
 
 
-class EnvSpec(object):
+class EnvSpec:
+    """(observation_dim, action_dim, horizon) -- positional arguments as in the reference's constructor."""
+    __slots__ = ("observation_dim", "action_dim", "horizon")
+
     def __init__(self, obs_dim, act_dim, horizon):
-        self.observation_dim = obs_dim
-        self.action_dim = act_dim
-        self.horizon = horizon
+        self.observation_dim, self.action_dim, self.horizon = int(obs_dim), int(act_dim), horizon
+
+    def __repr__(self):
+        return "EnvSpec(obs_dim=%d, act_dim=%d, horizon=%r)" % (self.observation_dim, self.action_dim, self.horizon)
