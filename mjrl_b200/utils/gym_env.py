@@ -4,7 +4,6 @@ baseline.  Environments / MuJoCo stepping stay on the host in mjrl itself (out o
 
 class EnvSpec:
     """(observation_dim, action_dim, horizon) -- positional arguments as in the reference's constructor."""
-    __slots__ = ("observation_dim", "action_dim", "horizon")
 
     def __init__(self, obs_dim, act_dim, horizon):
         self.observation_dim, self.action_dim, self.horizon = int(obs_dim), int(act_dim), horizon
