@@ -159,7 +159,10 @@ def test_baseline_fit(case, cluster, cuda_device):
     err = eng.vf_fit(g["fit_perms"][:2], 64, 1e-3, 1e-3, return_errors=True)
     np.testing.assert_allclose(err, g["fit1_err"], rtol=2e-4)
     w, mm, vv, step = eng.vf_get_state()
-    assert rel(w, g["fit1_w"]) < 1e-3          # 220 chaotic Adam steps: summation order decides the 4th digit
+    # SURVEY 8(d) gate: weights rel <= 1e-4 after the first call with the same permutation.  Measured on B200
+    # (tools/fit_parity_report.py): <= 1.5e-5 for every kernel on every fixture of this test (summation order of
+    # 155-220 chaotic Adam steps decides the 5th digit)
+    assert rel(w, g["fit1_w"]) < 1e-4
     eng.vf_fit(g["fit_perms"][2:4], 64, 1e-3, 1e-3)
     w, mm, vv, step = eng.vf_get_state()
     assert step == int(g["fit2_step"])
