@@ -12,9 +12,13 @@ events on the engine's stream, max over ranks); `e2e` times the public drop-in A
 from host float64 path dicts, host<->device copies included.  Strong scaling: the 1e6-timestep batch is sharded
 by trajectory over the ranks; one NCCL all-reduce of the flat gradient and of every FVP result.
 
-`--impl reference` (and the `cpu_baseline` object of the default arm) time the CPU restatement of the reference
-(oracle/npg_oracle.py, torch-autograd flavour: two forwards + double backward per FVP, per-path Python loops,
-sequential Adam) on the box's host cores on a bounded sample of the same workload.
+`--impl reference` (and the `cpu_baseline` object of the default arm) time the UNMODIFIED reference package
+(aravindr93/mjrl imported through oracle/ref_shim.py from baseline/_ref; the oracle restatement only when no copy of
+the reference is present) on the box's host cores, with the torch thread count calibrated on the box: the reference
+arm times one step on the full batch plus bounded-sample steps, `cpu_baseline` a bounded sample.
+
+The default line also carries `roofline_hbm`: the HBM-bound Fisher-vector product of the linear policy at
+BASELINE.json's cfg5 shape (376-dim observations, 5e5 timesteps), measured in the same run.
 """
 import argparse
 import json
@@ -119,14 +123,64 @@ def load_peaks():
 
 
 # ======================================================================================= CPU reference arm
-def cpu_reference_step_fn(cfg, n_traj_sample):
-    """Returns (step_fn, n_samples): one post-rollout step of the CPU restatement on `n_traj_sample` trajectories."""
+def _reference_or_port():
+    """The real aravindr93/mjrl package (through oracle/ref_shim.py: $MJRL_REF -> /root/reference -> baseline/_ref, the
+    offline `pip install --target` of the unmodified reference that travels to the GPU box) or, when no copy exists,
+    the oracle restatement."""
+    from oracle import ref_shim                 # the CPU baseline legs are the one place bench.py runs oracle/
+    if ref_shim.available():
+        return ref_shim.load(), "reference"
+    return None, "port"
+
+
+def cpu_reference_step_fn(cfg, n_traj_sample, capture=None):
+    """Returns (step_fn, n_samples, kind): one post-rollout step (batch_reinforce.py:94-112: compute_returns ->
+    compute_advantages -> train_from_paths -> baseline.fit) of the CPU reference on `n_traj_sample` trajectories."""
+    import contextlib
+    import io
     import torch
-    from oracle import npg_oracle as O          # the CPU baseline leg is the one place bench.py runs the oracle
+    R, kind = _reference_or_port()
     paths0 = make_paths(cfg, 0, n_traj_sample)
+    demo = make_paths(cfg, 10 ** 6, max(1, n_traj_sample // 40)) if cfg["algo"] == "dapg" else None
+    if kind == "reference":
+        es = R.EnvSpec(cfg["obs"], cfg["act"], cfg["horizon"])
+        pol = R.LinearPolicy(es, seed=500) if len(cfg["hidden"]) == 0 else R.MLP(es, hidden_sizes=cfg["hidden"], seed=500)
+        torch.manual_seed(1)
+        bl = R.MLPBaseline(es, **VF)
+        kw = dict(FIM_invert_args={"iters": CG_ITERS, "damping": DAMPING}, save_logs=False)
+        if cfg["algo"] == "trpo":
+            agent = R.TRPO(None, pol, bl, kl_dist=KL_DIST, **kw)
+        elif cfg["algo"] == "dapg":
+            agent = R.DAPG(None, pol, bl, demo_paths=demo, kl_dist=KL_DIST, **kw)
+        else:
+            agent = R.NPG(None, pol, bl, normalized_step_size=NPG_STEP, **kw)
+        if capture is not None:
+            capture["policy"], capture["baseline"] = pol, bl
+
+        def step():
+            paths = [dict(p) for p in paths0]
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):        # trpo.py:117-118 prints one line per backtrack
+                R.process_samples.compute_returns(paths, GAMMA)
+                R.process_samples.compute_advantages(paths, bl, GAMMA, LAM)
+                agent.train_from_paths(paths)
+                bl.fit(paths)
+            return {"backtracks": buf.getvalue().count("Backtracking")}
+
+        def fvp_time(reps=3):
+            obs = np.concatenate([p["observations"] for p in paths0])
+            act = np.concatenate([p["actions"] for p in paths0])
+            v = np.random.RandomState(1).randn(pol.d).astype(np.float32)
+            agent.HVP(obs, act, v, DAMPING)
+            t0 = time.time()
+            for _ in range(reps):
+                agent.HVP(obs, act, v, DAMPING)
+            return (time.time() - t0) / reps
+        return step, n_traj_sample * cfg["horizon"], kind, fvp_time
+
+    from oracle import npg_oracle as O
     spec = O.PolicySpec(cfg["obs"], cfg["act"], cfg["hidden"])
     state = dict(theta=O.init_policy_params(spec, 500), vf=O.VFState(cfg["obs"], (128, 128), seed=1))
-    demo = make_paths(cfg, 10 ** 6, max(1, n_traj_sample // 40)) if cfg["algo"] == "dapg" else None
 
     def step():
         paths = [dict(p) for p in paths0]
@@ -144,52 +198,135 @@ def cpu_reference_step_fn(cfg, n_traj_sample):
         state["theta"] = out["new_params"]
         perm = [np.random.permutation(obs.shape[0]) for _ in range(VF["epochs"])]
         O.vf_fit_torch(state["vf"], paths, perm, VF["epochs"], VF["batch_size"], VF["learn_rate"], VF["reg_coef"])
-        return out
+        return {"backtracks": int(out.get("backtracks", 0))}
 
-    return step, n_traj_sample * cfg["horizon"]
+    def fvp_time(reps=3):
+        obs = np.concatenate([p["observations"] for p in paths0])
+        v = np.random.RandomState(1).randn(spec.d).astype(np.float32)
+        O.fvp(spec, state["theta"], obs, v, DAMPING, torch.float32, autograd=True)
+        t0 = time.time()
+        for _ in range(reps):
+            O.fvp(spec, state["theta"], obs, v, DAMPING, torch.float32, autograd=True)
+        return (time.time() - t0) / reps
+    return step, n_traj_sample * cfg["horizon"], kind, fvp_time
 
 
-def cpu_fvp_time(cfg, n_traj_sample, reps=3):
+def pick_cpu_threads(cfg):
+    """The reference is torch-on-CPU: intra-op threads are the only parallelism it has.  More threads is not faster on
+    a many-core host (round 1: 64 threads were 2-4x slower than 8), so the thread count is calibrated on one FVP of a
+    small sample and the fastest count is used for every timed step; the table is reported."""
     import torch
-    from oracle import npg_oracle as O
-    paths = make_paths(cfg, 0, n_traj_sample)
-    spec = O.PolicySpec(cfg["obs"], cfg["act"], cfg["hidden"])
-    theta = O.init_policy_params(spec, 500)
-    obs = np.concatenate([p["observations"] for p in paths])
-    v = np.random.RandomState(1).randn(spec.d).astype(np.float32)
-    O.fvp(spec, theta, obs, v, DAMPING, torch.float32, autograd=True)
-    t0 = time.time()
-    for _ in range(reps):
-        O.fvp(spec, theta, obs, v, DAMPING, torch.float32, autograd=True)
-    return (time.time() - t0) / reps
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (min(8, ncpu), 16, 32, ncpu // 2, ncpu) if 1 <= c <= ncpu})
+    step, n, kind, fvp_time = cpu_reference_step_fn(cfg, max(2, 20000 // cfg["horizon"]))
+    table = {}
+    for c in cands:
+        torch.set_num_threads(c)
+        table[c] = fvp_time(reps=2)
+    best = min(table, key=table.get)
+    torch.set_num_threads(best)
+    return best, {str(k): round(v, 4) for k, v in table.items()}
 
 
 def run_reference(args, cfg, rank, world):
     if rank != 0:
         return
-    import torch
-    n_s = min(cfg["n_traj"], max(5, 100000 // cfg["horizon"]))      # <= 1e5 timesteps: large enough to be in the linear regime
-    step, n = cpu_reference_step_fn(cfg, n_s)
+    threads, table = pick_cpu_threads(cfg)
+    n_full = cfg["n_traj"]
+    n_s = min(cfg["n_traj"], max(5, 50000 // cfg["horizon"]))       # bounded sample for the warm-up / extra steps
+    step_s, n, kind, fvp_time = cpu_reference_step_fn(cfg, n_s)
     for _ in range(args.warmup):
-        step()
+        step_s()
+    # timed region: ONE step on the full batch (no extrapolation) + (steps-1) steps on the bounded sample
+    full_s, backtracks = None, None
+    if not args.reference_sample_only:
+        step_f, n_f, _, _ = cpu_reference_step_fn(cfg, n_full)
+        t0 = time.time()
+        r = step_f()
+        full_s = time.time() - t0
+        backtracks = r["backtracks"]
+        del step_f
     t0 = time.time()
-    for _ in range(args.steps):
-        step()
-    dt = (time.time() - t0) / args.steps
+    k = max(1, args.steps - 1)
+    for _ in range(k):
+        step_s()
+    dt_s = (time.time() - t0) / k
     scale = (cfg["n_traj"] * cfg["horizon"]) / n
-    value = 1.0 / (dt * scale)
-    fvp_t = cpu_fvp_time(cfg, n_s) * scale
-    cores = torch.get_num_threads()
-    sample = ("%d of %d trajectories (%d timesteps) per step; time extrapolated linearly x%.0f to the full batch"
-              % (n_s, cfg["n_traj"], n, scale))
+    sec_per_step = full_s if full_s is not None else dt_s * scale
+    value = 1.0 / sec_per_step
+    fvp_t = fvp_time() * scale
+    sample = ("1 timed step on the FULL batch (%d trajectories, %d timesteps, no extrapolation) = %.1f s; plus %d steps on "
+              "%d trajectories (%d timesteps) = %.2f s each, x%.0f = %.1f s extrapolated (cross-check only)"
+              % (n_full, n_full * cfg["horizon"], full_s, k, n_s, n, dt_s, scale, dt_s * scale)) if full_s is not None else \
+             ("%d of %d trajectories (%d timesteps) per step; extrapolated linearly x%.0f" % (n_s, cfg["n_traj"], n, scale))
     line = {"impl": "reference", "metric": "train_step_per_sec", "value": value, "unit": "train_step/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * scale * 1e3, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(cfg, args, world), "fvp_per_sec": 1.0 / fvp_t,
-            "cpu_baseline": {"value": value, "unit": "train_step/s", "cores": cores, "os_cpu_count": os.cpu_count(),
-                             "kind": "port", "sample": sample},
+            "trpo_backtracks_full_batch": backtracks,
+            "cpu_baseline": {"value": value, "unit": "train_step/s", "cores": threads, "os_cpu_count": os.cpu_count(),
+                             "kind": kind, "sample": sample, "thread_calibration_s_per_fvp": table,
+                             "extrapolated_from_sample_ms": dt_s * scale * 1e3},
             "e2e": {"value": value, "unit": "train_step/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def gpu_first_step_backtracks(cfg, n_traj_sample, cap):
+    """First update_from_paths of the GPU engine on the CPU baseline's sample, from the reference objects' own initial
+    policy parameters and baseline weights: returns the TRPO backtrack count (None for the other algorithms)."""
+    if cfg["algo"] != "trpo":
+        return None
+    from mjrl_b200.algos.trpo import TRPO
+    from mjrl_b200.baselines.mlp_baseline import MLPBaseline
+    from mjrl_b200.policies.gaussian_mlp import MLP
+    from mjrl_b200.utils.gym_env import EnvSpec
+    es = EnvSpec(cfg["obs"], cfg["act"], cfg["horizon"])
+    pol = MLP(es, hidden_sizes=cfg["hidden"], seed=500)
+    pol.set_param_values(cap["policy"].get_param_values(), set_new=True, set_old=True)
+    bl = MLPBaseline(es, **VF)
+    bl.set_flat_weights(np.concatenate([p.data.numpy().ravel() for p in cap["baseline"].model.parameters()]))
+    agent = TRPO(None, pol, bl, kl_dist=KL_DIST, FIM_invert_args={"iters": CG_ITERS, "damping": DAMPING})
+    agent.verbose = False
+    agent.update_from_paths([dict(p) for p in make_paths(cfg, 0, n_traj_sample)], GAMMA, LAM)
+    return int(agent.last_step.backtracks)
+
+
+def hbm_roofline_cfg5(peaks, reps=20):
+    """The HBM-bound kernel of the path (the north_star's HBM target is defined on cfg5): Fisher-vector
+    product of the linear policy, 5e5 timesteps x 376 observations = 752 MB streamed once per launch (> L2)."""
+    from mjrl_b200.engine import Engine
+    c5 = CONFIGS["cfg5"]
+    n = c5["n_traj"] * c5["horizon"]
+    rng = np.random.RandomState(5)
+    eng = Engine(c5["obs"], c5["act"], (), max_samples=n + 8, max_paths=c5["n_traj"] + 8)
+    obs = rng.standard_normal((n, c5["obs"]))
+    eng.upload_flat(obs, rng.standard_normal((n, c5["act"])), np.zeros(n), np.full(c5["n_traj"], c5["horizon"], np.int32),
+                    np.zeros(c5["n_traj"], np.uint8))
+    del obs
+    theta = (0.01 * rng.standard_normal(eng.d)).astype(np.float32)
+    theta[-c5["act"]:] = 0.0
+    eng.set_params(theta)
+    v = rng.standard_normal(eng.d).astype(np.float32)
+    tc = bool(eng.set_tensor_cores(True))
+    ms = []
+    for i in range(reps + 3):
+        eng.fvp(v, DAMPING)
+        if i >= 3:
+            ms.append(eng.last_fvp_ms())
+    eng.close()
+    t = float(np.mean(ms)) * 1e-3
+    by = 4.0 * n * c5["obs"]
+    prof = {}
+    pj = os.path.join(ROOT, "profiles", "fvp_ncu_cfg5.json")
+    if os.path.exists(pj):
+        prof = json.load(open(pj))
+    return {"bound": "hbm", "achieved": by / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": by / t / 1e9 / peaks["hbm_gbs"], "traffic": prof.get("dram_bytes_per_launch"),
+            "kernel": "linear_tc_kernel (tcgen05)" if tc else "linear_kernel<AG,MODE_FVP> (fp32 FMA)",
+            "workload": c5["name"], "launch_ms": t * 1e3, "launch_ms_min": float(np.min(ms)), "launches_timed": reps,
+            "algorithmic_bytes_per_launch": by, "peak_source": peaks["source"] + "; copy bandwidth",
+            "note": "kernel timed alone (CUDA events on the engine stream around the launch); the 752 MB observation "
+                    "matrix exceeds L2, so every launch streams it from HBM"}
 
 
 def workload_config(cfg, args, world):
@@ -227,7 +364,12 @@ def run_gpu(args, cfg, rank, world, local_rank):
     paths = make_paths(cfg, first, per[rank])
     n_local = per[rank] * cfg["horizon"]
     n_glob = cfg["n_traj"] * cfg["horizon"]
-    demo = make_paths(cfg, 10 ** 6 + first, max(1, per[rank] // 40)) if cfg["algo"] == "dapg" else None
+    # every rank is constructed with the SAME demonstration list; the agent keeps its shard (DAPG._local_demos)
+    demo_all = make_paths(cfg, 10 ** 6, max(1, cfg["n_traj"] // 40)) if cfg["algo"] == "dapg" else None
+    demo = None
+    if demo_all is not None:
+        from mjrl_b200.parallel import shard_paths
+        demo = shard_paths(demo_all, world, rank) if world > 1 else demo_all
 
     es = EnvSpec(cfg["obs"], cfg["act"], cfg["horizon"])
     pol = LinearPolicy(es, seed=500) if len(cfg["hidden"]) == 0 else MLP(es, hidden_sizes=cfg["hidden"], seed=500)
@@ -238,7 +380,7 @@ def run_gpu(args, cfg, rank, world, local_rank):
         agent = TRPO(None, pol, bl, kl_dist=KL_DIST, **kw)
         agent.verbose = False            # the reference prints one line per backtrack; stdout carries the JSON line here
     elif cfg["algo"] == "dapg":
-        agent = DAPG(None, pol, bl, demo_paths=demo, kl_dist=KL_DIST, **kw)
+        agent = DAPG(None, pol, bl, demo_paths=demo_all, kl_dist=KL_DIST, **kw)
     else:
         agent = NPG(None, pol, bl, normalized_step_size=NPG_STEP, **kw)
     eng = agent._eng(n_local + (sum(len(p["actions"]) for p in demo) if demo else 0), len(paths))
@@ -302,6 +444,8 @@ def run_gpu(args, cfg, rank, world, local_rank):
     ms = max_over_ranks(ms)
     ms_per_step = ms / args.steps
     fvp_ms_kernel = float(np.mean([s.fvp_kernel_ms_sum / max(1, s.fvp_launches) for s in stats]))
+    fit_steps = n_glob // VF["batch_size"] - 1
+    fit_us = eng.last_fit_ms() * 1e3 / max(1, fit_steps * VF["epochs"])
     backtracks = [int(s.backtracks) for s in stats]
     phase = {k: float(np.mean([getattr(s, k) for s in stats])) for k in ("time_vpg_ms", "time_npg_ms", "time_eval_ms")}
 
@@ -319,7 +463,7 @@ def run_gpu(args, cfg, rank, world, local_rank):
 
     # ---------------- e2e: public API from host float64 path dicts ----------------
     def e2e_step():
-        fresh = [dict(p) for p in paths]                 # new list object => uploaded again, dicts re-populated
+        fresh = [dict(p) for p in paths]                 # the dicts are re-populated; update_from_paths uploads per call
         agent.update_from_paths(fresh, GAMMA, LAM)
 
     e2e_warm = max(1, min(args.warmup, 3))
@@ -327,14 +471,24 @@ def run_gpu(args, cfg, rank, world, local_rank):
     for _ in range(e2e_warm):
         e2e_step()
     barrier()
+    tr0 = eng.transfer_stats()
     t0 = time.time()
     for _ in range(e2e_steps):
         e2e_step()
     barrier()
     e2e_s = max_over_ranks((time.time() - t0) / e2e_steps)
-    demo_n = sum(len(p["actions"]) for p in demo) if demo else 0
-    h2d = n_local * (cfg["obs"] + cfg["act"] + 1) * 8 + demo_n * (cfg["obs"] + cfg["act"]) * 8 + n_glob * 4 * VF["epochs"]
-    d2h = n_local * (8 + 4 + 8) + eng.d * 4 + 3 * eng.vf_d * 4
+    tr1 = eng.transfer_stats()
+    # bytes the ENGINE copied (library counters, mjb_transfer_stats), not a formula; uploads must equal the steps
+    h2d = (tr1[0] - tr0[0]) / e2e_steps
+    d2h = (tr1[1] - tr0[1]) / e2e_steps
+    uploads = tr1[2] - tr0[2]
+    expect_uploads = e2e_steps * (2 if demo else 1)
+    if uploads != expect_uploads:
+        raise SystemExit("e2e: %d trajectory uploads in %d steps (expected %d) -- the timed region skipped its H2D copy"
+                         % (uploads, e2e_steps, expect_uploads))
+    min_h2d = n_local * (cfg["obs"] + cfg["act"] + 1) * 8
+    if h2d < min_h2d:
+        raise SystemExit("e2e: %.0f B/step copied host->device, the trajectories alone are %d B" % (h2d, min_h2d))
 
     if rank != 0:
         runtime.shutdown()
@@ -379,22 +533,33 @@ def run_gpu(args, cfg, rank, world, local_rank):
                          "(tensor-core fit kernel: 1 SM, FVP on 147; cluster fallback: 16 SMs); achieved counts ALGORITHMIC flops (10P-4P1 per timestep), not the 3x split MMAs"})
 
     # ---------------- CPU baseline (bounded sample, rank 0, N=1 only) ----------------
-    cpu = None
+    cpu, bt_check, hbm = None, None, None
     if world == 1 and not args.no_cpu_baseline:
+        threads, table = pick_cpu_threads(cfg)
         n_s = min(cfg["n_traj"], max(5, 100000 // cfg["horizon"]))
-        step, n = cpu_reference_step_fn(cfg, n_s)
-        step()
+        cap = {}
+        step, n, kind, fvp_time = cpu_reference_step_fn(cfg, n_s, capture=cap)
+        # TRPO caveat: the line search is data dependent -- same sample, same initial policy and baseline
+        # on the GPU engine, backtrack counts of the first step must agree
+        gpu_bt = gpu_first_step_backtracks(cfg, n_s, cap) if kind == "reference" else None
+        r0 = step()
+        if gpu_bt is not None:
+            bt_check = {"sample_trajectories": n_s, "cpu_reference": int(r0["backtracks"]), "gpu": int(gpu_bt),
+                        "equal": int(r0["backtracks"]) == int(gpu_bt)}
         t0 = time.time()
         reps_cpu = 2
         for _ in range(reps_cpu):
             step()
         dt = (time.time() - t0) / reps_cpu
         scale = n_glob / n
-        cpu = {"value": 1.0 / (dt * scale), "unit": "train_step/s", "cores": torch.get_num_threads(),
-               "os_cpu_count": os.cpu_count(), "kind": "port",
+        cpu = {"value": 1.0 / (dt * scale), "unit": "train_step/s", "cores": threads,
+               "os_cpu_count": os.cpu_count(), "kind": kind, "thread_calibration_s_per_fvp": table,
                "sample": "%d of %d trajectories (%d timesteps), %d timed steps after 1 warm-up; extrapolated linearly x%.0f"
                          % (n_s, cfg["n_traj"], n, reps_cpu, scale),
-               "fvp_per_sec": 1.0 / (cpu_fvp_time(cfg, n_s) * scale)}
+               "fvp_per_sec": 1.0 / (fvp_time() * scale)}
+    if world == 1 and not args.no_hbm_roofline and args.config != "cfg5":
+        runtime.shutdown()
+        hbm = hbm_roofline_cfg5(peaks)
 
     line = {"metric": "train_step_per_sec", "value": 1e3 / ms_per_step, "unit": "train_step/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -402,11 +567,14 @@ def run_gpu(args, cfg, rank, world, local_rank):
             "config": workload_config(cfg, args, world), "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": 1.0 / e2e_s, "unit": "train_step/s", "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "bytes_source": "mjb_transfer_stats counter deltas over the timed e2e steps (rank 0 shard)",
+                    "uploads_in_timed_region": int(uploads),
                     "api": "mjrl_b200.algos.%s.update_from_paths(paths) on host float64 path dicts (per rank shard)"
                            % {"npg": "npg_cg.NPG", "trpo": "trpo.TRPO", "dapg": "dapg.DAPG"}[cfg["algo"]]},
             "fvp_per_sec": fvp_per_sec, "fvp_ms_in_cg": cg_ms / CG_ITERS, "fvp_kernel_ms": fvp_ms_kernel,
             "wall_ms_per_step": wall / args.steps * 1e3, "phase_ms": phase, "trpo_backtracks": backtracks,
-            "roofline": roof, "cpu_baseline": cpu}
+            "fit_us_per_adam_step": fit_us, "fit_adam_steps": fit_steps,
+            "roofline": roof, "roofline_hbm": hbm, "cpu_baseline": cpu, "trpo_backtrack_check": bt_check}
     print(json.dumps(line), flush=True)
     runtime.shutdown()
     if dist is not None:
@@ -421,6 +589,9 @@ def main():
     ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hbm-roofline", action="store_true", help="skip the cfg5 linear-policy FVP measurement")
+    ap.add_argument("--reference-sample-only", action="store_true",
+                    help="--impl reference: skip the full-batch step (bounded sample + extrapolation only)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))

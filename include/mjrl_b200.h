@@ -165,15 +165,10 @@ int  mjb_vf_fit(mjb_engine* e, const int32_t* perms, int epochs, int batch_size,
 int  mjb_vf_fit_begin(mjb_engine* e, const int32_t* perms, int epochs, int batch_size, float lr, float reg_coef,
                       double* err_before);
 int  mjb_vf_fit_end(mjb_engine* e, double* err_after);
-/* Execution shape of the fit.
- * cluster_ctas 1 (default) = the single-SM tcgen05 kernel (128x128 hidden, <= 32 input features, batch 64); shapes
- *   it does not cover fall back to the 16-CTA cluster kernels automatically.
- * cluster_ctas 8 or 16 = one thread-block cluster of that many CTAs:
- *   model_parallel = 1: hidden units split over the cluster -- weights and Adam moments stay in their owner's
- *                      shared memory, activation slices cross distributed shared memory;
- *   model_parallel = 0: minibatch rows split over the cluster, gradients exchanged through L2;
- * cluster_ctas 0 = single-CTA fp32-FMA kernel (also the last fallback for shapes no other kernel covers). */
-int  mjb_vf_set_cluster(mjb_engine* e, int cluster_ctas, int model_parallel);
+/* Fit arithmetic: 1 (default) = the single-SM tcgen05 kernel where the shape allows (128x128 hidden, batch 64, input
+ * features within the kernel's shared-memory budget); 0 = the single-CTA fp32-FMA kernel, which is also the fallback
+ * for every shape the tensor-core kernel does not cover (utils/optimize_model.py:7-36 semantics in both). */
+int  mjb_vf_set_tensor_cores(mjb_engine* e, int on);
 
 /* ---- host helper ---------------------------------------------------------------------------- */
 /* np.random.permutation(n) of numpy's global legacy RandomState, bit for bit: the minibatch order MLPBaseline.fit
@@ -188,7 +183,22 @@ int  mjb_host_permutation(uint32_t* mt_key624, int32_t* mt_pos, int64_t n, int32
 int  mjb_event_record(mjb_engine* e, int slot);
 int  mjb_event_elapsed_ms(mjb_engine* e, int slot_a, int slot_b, float* ms);   /* synchronises on slot_b */
 int64_t mjb_kernel_launches(const mjb_engine* e);        /* kernels launched by this engine so far    */
+/* Host<->device traffic this engine has issued so far: bytes copied from host memory into the engine (trajectory
+ * uploads, parameters, permutations ...), bytes copied back to host memory, and the number of trajectory uploads
+ * (mjb_batch_upload / _flat calls that completed).  Benchmarks report per-step deltas of these counters. */
+typedef struct mjb_transfer_stats_t { int64_t h2d_bytes, d2h_bytes, uploads; } mjb_transfer_stats_t;
+int  mjb_transfer_stats(const mjb_engine* e, mjb_transfer_stats_t* out);
 int  mjb_fvp_timing(mjb_engine* e, float* last_ms);       /* CUDA-event time of the last FVP kernel    */
+/* CUDA-event time of the sequential Adam kernels of the last fit (all epochs), on the stream they ran on; joins a fit
+ * in flight.  Divided by epochs x (N/batch - 1) it is the per-Adam-step latency of utils/optimize_model.py:24-35. */
+int  mjb_vf_fit_timing(mjb_engine* e, float* last_ms);
+
+
+/* ---- developer aids (used by tools/, not by the Python mirror) ---------------------------------- */
+/* per-phase clock64 counters of the tensor-core fit kernel / of the linear-policy FVP kernel: enable = 1 arms the
+ * counters, enable = 0 reads them back (16 resp. 8 values) and disarms. */
+int  mjb_dev_vf_profile(mjb_engine* e, long long* out16, int enable);
+int  mjb_dev_lin_profile(mjb_engine* e, long long* out8, int enable);
 
 #ifdef __cplusplus
 }

@@ -35,6 +35,10 @@ class BatchStats(C.Structure):
                 ("n_samples_global", C.c_int64)]
 
 
+class TransferStats(C.Structure):
+    _fields_ = [("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("uploads", C.c_int64)]
+
+
 # name -> (restype, argtypes); every symbol of include/mjrl_b200.h is listed (tests check the header against this)
 _P = C.c_void_p
 _SIGNATURES = {
@@ -79,12 +83,16 @@ _SIGNATURES = {
     "mjb_vf_fit": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_double * 2)]),
     "mjb_vf_fit_begin": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_double)]),
     "mjb_vf_fit_end": (C.c_int, [_P, C.POINTER(C.c_double)]),
-    "mjb_vf_set_cluster": (C.c_int, [_P, C.c_int, C.c_int]),
+    "mjb_vf_set_tensor_cores": (C.c_int, [_P, C.c_int]),
     "mjb_event_record": (C.c_int, [_P, C.c_int]),
     "mjb_event_elapsed_ms": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "mjb_kernel_launches": (C.c_int64, [_P]),
     "mjb_host_permutation": (C.c_int, [_P, C.POINTER(C.c_int32), C.c_int64, _P]),
     "mjb_fvp_timing": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "mjb_vf_fit_timing": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "mjb_transfer_stats": (C.c_int, [_P, C.POINTER(TransferStats)]),
+    "mjb_dev_vf_profile": (C.c_int, [_P, _P, C.c_int]),
+    "mjb_dev_lin_profile": (C.c_int, [_P, _P, C.c_int]),
 }
 
 _lib = None

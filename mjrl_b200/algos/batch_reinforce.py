@@ -60,6 +60,9 @@ class BatchREINFORCE:
         self._pushed = sig
 
     def _resident(self, paths):
+        """The engine holding `paths` as its rollout batch: inside runtime.session (update_from_paths) the pinned batch
+        is reused, everywhere else the trajectories are uploaded again -- like the reference, a call always works on
+        the arrays it is handed."""
         n = int(sum(len(p["rewards"]) for p in paths))
         eng = self._eng(n + self._demo_samples(), len(paths))
         runtime.ensure_resident(eng, paths)
@@ -69,15 +72,17 @@ class BatchREINFORCE:
     def _demo_samples(self):
         return 0
 
-    def _flat_batch(self, observations, actions, advantages=None):
-        """For the reference-signature helpers that take concatenated arrays: make them the resident batch."""
+    def _flat_batch(self, observations, actions, advantages=None, token=None):
+        """For the reference-signature helpers that take concatenated arrays: upload them as the rollout batch.  Always
+        uploads, except for the holder of `token` = (engine, generation) of an upload it made itself with exactly these
+        array objects (build_Hvp_eval's closure: ten products over one batch) while no other upload happened since."""
         n = observations.shape[0]
         eng = self._eng(n, 1)
-        key = ("flat", id(observations), id(actions), n)
-        if getattr(eng, "resident", None) != key:
+        reuse = (token is not None and token[0] is eng and token[1] == eng.generation
+                 and token[2] is observations and token[3] is actions)
+        if not reuse:
+            eng.session_paths = None
             eng.upload_flat(observations, actions, np.zeros(n), np.array([n], np.int32), np.zeros(1, np.uint8))
-            eng.resident = key
-            eng.have_returns = False
         self._push_policy(eng)
         if advantages is not None:
             eng.set_white(np.asarray(advantages, np.float32))   # the reference passes whitened advantages here
@@ -124,33 +129,51 @@ class BatchREINFORCE:
 
     def update_from_paths(self, paths, gamma=0.995, gae_lambda=0.97):
         """Everything train_step does after sampling (batch_reinforce.py:94-112) on one resident device batch."""
-        eng = self._resident(paths)
-        overlap = hasattr(self.baseline, "fit_begin")
+        n = int(sum(len(p["rewards"]) for p in paths))
+        eng = self._eng(n + self._demo_samples(), len(paths))
+        with runtime.session(eng, paths):                    # ONE upload per call, always; pinned for the nested helpers
+            self._push_policy(eng)
+            return self._update_resident(eng, paths, gamma, gae_lambda)
+
+    def _update_resident(self, eng, paths, gamma, gae_lambda):
+        # The sequential baseline fit is the longest chain of the step and depends only on the returns: it is started
+        # right away on the engine's side stream; the write-back of the returns, the advantages (with the PRE-fit
+        # baseline, as in the reference's program order) and the policy update run concurrently.  With
+        # hvp_sample_frac < 1 the reference interleaves host RNG draws (one index set per Fisher product actually
+        # evaluated, then the fit permutations, A9); that order is only reproducible with the fit AFTER the policy
+        # step, so the overlap is switched off for that setting.
+        subsampling = getattr(self, "hvp_subsample", None) is not None and self.hvp_subsample < 0.99
+        overlap = hasattr(self.baseline, "fit_begin") and not subsampling
         process_samples.returns_on(eng, paths, gamma, write_back=not overlap)
-        ts = timer.time()
-        if overlap:
-            # The sequential baseline fit is the longest chain of the step and depends only on the returns: start it
-            # right away on the engine's side stream; the write-back of the returns, the advantages (with the PRE-fit
-            # baseline, as in the reference's program order) and the policy update run concurrently.  Host RNG draws
-            # keep the reference's order (A9): the FVP subsample indices of this step first, then the fit permutations.
-            self._pending_hvp_idx = self._draw_hvp_indices(eng.n, self.FIM_invert_args['iters']) \
-                if hasattr(self, "_draw_hvp_indices") else None
-            self._hvp_idx_drawn = True
-            self.baseline._bind(eng)
-            error_before = self.baseline.fit_begin(paths, return_errors=self.save_logs)
-            process_samples.returns_write_back(eng, paths)
-        process_samples.advantages_on(eng, paths, self.baseline, gamma, gae_lambda, fit_in_flight=overlap)
-        eval_statistics = self.train_from_paths(paths)
+        error_before = error_after = None
+        fit_started = False
+        try:
+            if overlap:
+                self.baseline._bind(eng)
+                error_before = self.baseline.fit_begin(paths, return_errors=self.save_logs)
+                fit_started = True
+                process_samples.returns_write_back(eng, paths)
+            process_samples.advantages_on(eng, paths, self.baseline, gamma, gae_lambda, fit_in_flight=overlap)
+            eval_statistics = self.train_from_paths(paths)
+        except BaseException:
+            if fit_started:                               # never leave a fit in flight behind a failed policy step
+                try:
+                    self.baseline.fit_end(return_errors=False)
+                except Exception:
+                    pass
+            raise
         if self.save_logs:
             self.logger.log_kv('num_samples', int(np.sum([p["rewards"].shape[0] for p in paths])))
+        ts = timer.time()
         if overlap:
             error_after = self.baseline.fit_end(return_errors=self.save_logs)
         elif self.save_logs:
-            ts = timer.time()
             error_before, error_after = self.baseline.fit(paths, return_errors=True)
         else:
             self.baseline.fit(paths)
         if self.save_logs:
+            # overlap mode: the fit ran concurrently with the policy update; time_VF is the wall time still spent
+            # waiting for it after train_from_paths returned (the reference logs the whole sequential fit here)
             self.logger.log_kv('time_VF', timer.time() - ts)
             self.logger.log_kv('VF_error_before', error_before)
             self.logger.log_kv('VF_error_after', error_after)
@@ -161,15 +184,13 @@ class BatchREINFORCE:
         """batch_reinforce.py:178-197: whitening + return statistics on the device; returns the reference's tuple
         except that the concatenated arrays stay on the GPU (None placeholders)."""
         eng = self._resident(paths)
-        if "advantages" in paths[0] and not self._adv_on_device(eng, paths):
+        if "advantages" in paths[0] and not eng.adv_on_device:
+            # anything but advantages the engine itself just computed for this very upload comes from the path dicts
             eng.set_advantages(np.concatenate([p["advantages"] for p in paths]))
         st = eng.process_paths()
         base_stats = [st.mean_return, st.std_return, st.min_return, st.max_return]
         running = st.mean_return if self.running_score is None else 0.9 * self.running_score + 0.1 * st.mean_return
         return None, None, None, base_stats, running
-
-    def _adv_on_device(self, eng, paths):
-        return getattr(eng, "adv_paths", None) == runtime.fingerprint(paths)
 
     def log_rollout_statistics(self, paths, base_stats=None):
         if base_stats is None:

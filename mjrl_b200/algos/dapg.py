@@ -27,6 +27,15 @@ class DAPG(NPG):
     def _demo_samples(self):
         return int(sum(len(p["actions"]) for p in self.demo_paths)) if self._use_demos() else 0
 
+    def _local_demos(self, eng):
+        """Under data parallelism the demonstrations are sharded like the rollout samples: every rank is
+        constructed with the SAME demo_paths list and keeps a contiguous range of it, so the all-reduced gradient counts
+        each demonstration sample once with weight 1e-2*lam/N (dapg.py:62-74,97-98), as on one GPU."""
+        if eng.world_size == 1:
+            return self.demo_paths
+        from mjrl_b200.parallel import shard_paths
+        return shard_paths(self.demo_paths, eng.world_size, eng.rank)
+
     def _step_args(self):
         return dict(step_size=self.kl_dist)
 
@@ -34,7 +43,7 @@ class DAPG(NPG):
         """Append the demonstrations behind the rollout samples and return lam_0*lam_1^iter (dapg.py:62-66)."""
         if not self._use_demos():
             return 0.0                      # gradient over the rollout batch only, step still 2*kl_dist
-        eng.upload_paths(self.demo_paths, which=DEMO)
+        eng.upload_paths(self._local_demos(eng), which=DEMO)
         lam = self.lam_0 * (self.lam_1 ** self.iter_count)
         self.iter_count += 1
         return lam

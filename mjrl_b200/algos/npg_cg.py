@@ -25,15 +25,22 @@ class NPG(BatchREINFORCE):
             self.input_normalization = None
 
     # ---- reference-signature Fisher-vector product (npg_cg.py:62-88) ----
-    def HVP(self, observations, actions, vector, regu_coef=None):
+    def HVP(self, observations, actions, vector, regu_coef=None, _token=None):
         regu_coef = self.FIM_invert_args['damping'] if regu_coef is None else regu_coef
-        eng = self._flat_batch(observations, actions)
+        eng = self._flat_batch(observations, actions, token=_token)
         idx = self._draw_hvp_indices(observations.shape[0], 1)
         return eng.fvp(vector, regu_coef, None if idx is None else idx[0])
 
     def build_Hvp_eval(self, inputs, regu_coef=None):
+        """npg_cg.py:83-88.  The closure uploads its batch on the first product and reuses it for the following ones
+        as long as nothing else was uploaded in between (engine generation counter + the same array objects)."""
+        state = {"token": None}
+
         def eval(v):
-            return self.HVP(*(inputs + [v] + [regu_coef]))
+            out = self.HVP(*(inputs + [v] + [regu_coef]), _token=state["token"])
+            eng = self._engine
+            state["token"] = (eng, eng.generation, inputs[0], inputs[1])
+            return out
         return eval
 
     def _draw_hvp_indices(self, n_local, iters):
@@ -76,11 +83,16 @@ class NPG(BatchREINFORCE):
             self._normalize_inputs(eng, paths)
         iters = self.FIM_invert_args['iters']
         demo_lam = self._demo_lam(eng)
-        if getattr(self, "_hvp_idx_drawn", False):          # drawn early by update_from_paths (RNG order, A9)
-            idx, self._hvp_idx_drawn = self._pending_hvp_idx, False
-        else:
-            idx = self._draw_hvp_indices(eng.n, iters)
+        # hvp_sample_frac < 1: the device-resident CG needs every index set up front, the reference draws one per
+        # product it actually evaluates (npg_cg.py:65-69, cg_solve.py:19-20 may stop early).  Draw all, and when the CG
+        # stopped early rewind the global RNG and redraw only the sets that were consumed, so every later host draw
+        # (the fit permutations) sees the reference's generator state.
+        rng_before = np.random.get_state()
+        idx = self._draw_hvp_indices(eng.n, iters)
         st = eng.step(self.algo, cg_iters=iters, damping=self.FIM_invert_args['damping'], demo_lam=demo_lam,
                       hvp_idx=idx, **self._step_args())
+        if idx is not None and st.cg_iters_run < iters:
+            np.random.set_state(rng_before)
+            self._draw_hvp_indices(eng.n, int(st.cg_iters_run))
         self._finish_step(eng, st, paths, timer.time() - t0)
         return base_stats

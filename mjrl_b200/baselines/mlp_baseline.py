@@ -105,10 +105,9 @@ class MLPBaseline:
         n = int(sum(len(p["rewards"]) for p in paths))
         eng = self._eng(n, len(paths))
         runtime.ensure_resident(eng, paths)
-        if not getattr(eng, "have_returns", False):
+        if not eng.have_returns:
             # returns were computed by someone else: the reference reads path["returns"] (mlp_baseline.py:64)
             eng.set_returns(np.concatenate([p["returns"] for p in paths]))
-            eng.have_returns = True
         n_glob = eng.n_global()
         # host RNG draw at the reference's program point (optimize_model.py:22): one permutation per epoch, from
         # numpy's global RandomState (bit-identical order and RNG state, see runtime.global_permutation)
@@ -122,7 +121,6 @@ class MLPBaseline:
 
     def predict(self, path):
         eng = self._eng(len(path["rewards"]), 1)
-        runtime.ensure_resident(eng, [path], force=True)
-        eng.resident = None
+        runtime.ensure_resident(eng, [path], force=True)     # replaces (and un-pins) whatever batch was resident
         eng.vf_predict()
         return eng.baseline()

@@ -69,6 +69,7 @@ struct mjb_engine {
     bool fit_in_flight = false;
     std::string err;
     long long launches = 0;
+    long long h2d_bytes = 0, d2h_bytes = 0, uploads = 0;   // host<->device traffic actually issued (mjb_transfer_stats)
     // ---- policy
     bool linear = false;
     int H = 0;
@@ -107,12 +108,10 @@ struct mjb_engine {
     int vfH = 0; PrepLayout VPL; int vf_d = 0;
     float *vf_w = nullptr, *vf_m = nullptr, *vf_v = nullptr, *vf_wT = nullptr, *vf_prep = nullptr;
     long long vf_step = 0;
-    float* vf_cl_scratch = nullptr;
     float* vf_feat = nullptr; float* vf_ret32 = nullptr; long long vf_feat_cap = 0;   // fp32 features / targets of the fit
-    int vf_cluster = 1;       // fit kernel: 1 = single-SM tensor-core kernel, 8/16 = cluster kernels, 0 = single-CTA FMA kernel
-    int vf_sms = 1;           // SMs the fit kernel in flight occupies (set at launch)
+    int vf_tc_on = 1;         // fit kernel: 1 = single-SM tensor-core kernel where the shape allows, 0 = single-CTA FMA kernel
+    int vf_sms = 1;           // SMs the fit kernel in flight occupies
     float2* vf_consts = nullptr; int vf_consts_cap = 0;   // per-step Adam constants of the fit kernels
-    int vf_model_parallel = 1; // 1: hidden units split over the cluster (vf_fit_mp.cu); 0: minibatch rows split (vf_fit_cluster.cu)
     int* perm_dev = nullptr; long long perm_cap = 0;
     // global (all-rank) copies used by the replicated fit when world_size > 1
     float* fit_obs = nullptr; int* fit_tstep = nullptr; double* fit_ret = nullptr; long long fit_cap = 0;
@@ -125,6 +124,8 @@ struct mjb_engine {
     cudaEvent_t fvp_ev[kFvpRing][2];
     long long fvp_count = 0;
     float last_fvp_ms = 0.f;
+    cudaEvent_t fit_ev[2] = {nullptr, nullptr};     // around the sequential Adam kernels of the last fit (on its stream)
+    bool fit_timed = false;
 };
 
 enum {  // slots in dsc
@@ -179,6 +180,18 @@ int dalloc(mjb_engine* e, T** p, size_t n) {
     return 0;
 }
 
+bool is_host_ptr(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged;
+}
+// user pointer -> engine buffer ("host-or-device" arguments of the C ABI); host sources are counted as H2D traffic
+int copy_in(mjb_engine* e, void* dst, const void* src, size_t bytes) {
+    if (is_host_ptr(src)) e->h2d_bytes += (long long)bytes;
+    CK(e, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, e->stream));
+    return 0;
+}
+
 int allreduce(mjb_engine* e, void* buf, size_t count, ncclDataType_t dt, ncclRedOp_t op = ncclSum) {
     if (!e->comm) return 0;
     NK(e, g_nccl.AllReduce(buf, buf, count, dt, op, e->comm, e->stream));
@@ -186,7 +199,7 @@ int allreduce(mjb_engine* e, void* buf, size_t count, ncclDataType_t dt, ncclRed
 }
 
 int set_params(mjb_engine* e, ParamSet& ps, const float* theta_src) {
-    if (theta_src) CK(e, cudaMemcpyAsync(ps.theta, theta_src, sizeof(float) * e->d, cudaMemcpyDefault, e->stream));
+    if (theta_src && copy_in(e, ps.theta, theta_src, sizeof(float) * e->d)) return -1;
     launch_clamp_tail(ps.theta, e->d, e->A, e->cfg.min_log_std, e->stream);
     if (e->linear) launch_prep_linear(ps.theta, e->LL, ps.prep, e->stream);
     else launch_prep_mlp(ps.theta, e->PL, ps.prep, e->stream);
@@ -214,7 +227,7 @@ int run_policy(mjb_engine* e, int mode, const ParamSet& ps, const float* tangent
     }
     const int MT = e->linear ? 128 : mlp_tile_rows_for(e->H);
     const long long tiles = (n + MT - 1) / MT;
-    // while the fit cluster is running on its own stream it owns vf_cluster SMs: size the persistent grid for the rest
+    // while the fit is running on its own stream it owns vf_sms SMs: size the persistent grid for the rest
     const int sms = e->num_sms - (e->fit_in_flight ? e->vf_sms : 0);
     int grid = (int)std::max<long long>(1, std::min<long long>(tiles, (long long)e->occ[mode] * sms));
     grid = std::min(grid, e->max_grid);
@@ -385,8 +398,7 @@ int cg_device(mjb_engine* e, const float* b, int iters, float damping, float tol
 
 int upload_idx(mjb_engine* e, const int32_t* idx, long long total) {
     if (ensure_idx(e, total)) return -1;
-    CK(e, cudaMemcpyAsync(e->idx_dev, idx, sizeof(int) * total, cudaMemcpyDefault, e->stream));
-    return 0;
+    return copy_in(e, e->idx_dev, idx, sizeof(int) * total);
 }
 
 }  // namespace
@@ -409,13 +421,14 @@ void mjb_destroy(mjb_engine* e) {
                     e->prep_tan, e->tc_prep_new, e->tc_prep_tan, e->tc_vscale, e->obs, e->act, e->rew, e->path_off, e->term, e->tstep, e->ret, e->adv, e->base,
                     e->adv_white, e->weights, e->path_ret, e->ll_old, e->mu_old, e->gpartial, e->eval_partial,
                     e->mom_scratch, e->dsc, e->g, e->x, e->r, e->p, e->Fp, e->tmpv, e->idx_dev, e->stage64, e->vf_w,
-                    e->vf_m, e->vf_v, e->vf_wT, e->vf_prep, e->vf_cl_scratch, e->vf_feat, e->vf_ret32, e->vf_consts, e->perm_dev, e->fit_obs, e->fit_tstep, e->fit_ret};
+                    e->vf_m, e->vf_v, e->vf_wT, e->vf_prep, e->vf_feat, e->vf_ret32, e->vf_consts, e->perm_dev, e->fit_obs, e->fit_tstep, e->fit_ret};
     for (void* b : bufs) if (b) cudaFree(b);
     if (e->pinned) cudaFreeHost(e->pinned);
     if (e->h_dsc) cudaFreeHost(e->h_dsc);
     for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : e->user_ev) if (ev) cudaEventDestroy(ev);
     for (auto& pr : e->fvp_ev) for (auto& ev : pr) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : e->fit_ev) if (ev) cudaEventDestroy(ev);
     if (e->stream_vf) { cudaStreamSynchronize(e->stream_vf); cudaStreamDestroy(e->stream_vf); }
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -447,6 +460,7 @@ int mjb_create(const mjb_config* cfg, mjb_engine** out) {
     for (auto& ev : e->ev) if (cudaEventCreate(&ev) != cudaSuccess) return fail("event create failed");
     for (auto& ev : e->user_ev) if (cudaEventCreate(&ev) != cudaSuccess) return fail("event create failed");
     for (auto& pr : e->fvp_ev) for (auto& ev : pr) if (cudaEventCreate(&ev) != cudaSuccess) return fail("event create failed");
+    for (auto& ev : e->fit_ev) if (cudaEventCreate(&ev) != cudaSuccess) return fail("event create failed");
 
     e->linear = cfg->n_hidden == 0;
     e->A = cfg->act_dim;
@@ -568,6 +582,7 @@ static int finish_upload(mjb_engine* e, int which, int n_paths, const int32_t* l
         e->n_demo = n;
     }
     e->old_cache_valid = false;
+    e->uploads += 1;
     return 0;
 }
 
@@ -575,7 +590,8 @@ int mjb_batch_upload(mjb_engine* e, int which, int32_t n_paths, const double* co
                      const double* const* rew, const int32_t* len, const uint8_t* terminated) {
     if (which != MJB_BATCH_ROLLOUT && which != MJB_BATCH_DEMO) FAIL(e, "bad batch id");
     if (n_paths < 0 || (which == MJB_BATCH_ROLLOUT && n_paths > e->cfg.max_paths)) FAIL(e, "too many paths for max_paths");
-    if (e->fit_in_flight && mjb_vf_fit_end(e, nullptr)) return -1;
+    // a fit in flight reads the rollout rows (or its own feature copy); demonstration rows live behind them
+    if (which == MJB_BATCH_ROLLOUT && e->fit_in_flight && mjb_vf_fit_end(e, nullptr)) return -1;
     long long n = 0;
     for (int i = 0; i < n_paths; ++i) { if (len[i] < 0) FAIL(e, "negative path length"); n += len[i]; }
     const long long row0 = which == MJB_BATCH_DEMO ? e->n_roll : 0;
@@ -605,6 +621,7 @@ int mjb_batch_upload(mjb_engine* e, int which, int32_t n_paths, const double* co
                 if (in_path == total) { ++pi; in_path = 0; }
             }
             CK(e, cudaMemcpyAsync(dst_dev + dev_off, pin, fill * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+            e->h2d_bytes += (long long)(fill * sizeof(double));
             CK(e, cudaEventRecord(done[slot], e->stream));
             used[slot] = 1;
             dev_off += fill;
@@ -621,41 +638,41 @@ int mjb_batch_upload_flat(mjb_engine* e, int which, int32_t n_paths, const doubl
                           const double* rew, const int32_t* len, const uint8_t* terminated) {
     if (which != MJB_BATCH_ROLLOUT && which != MJB_BATCH_DEMO) FAIL(e, "bad batch id");
     if (n_paths < 0 || (which == MJB_BATCH_ROLLOUT && n_paths > e->cfg.max_paths)) FAIL(e, "too many paths for max_paths");
-    if (e->fit_in_flight && mjb_vf_fit_end(e, nullptr)) return -1;
+    if (which == MJB_BATCH_ROLLOUT && e->fit_in_flight && mjb_vf_fit_end(e, nullptr)) return -1;
     long long n = 0;
     for (int i = 0; i < n_paths; ++i) n += len[i];
     const long long row0 = which == MJB_BATCH_DEMO ? e->n_roll : 0;
     if (row0 + n > e->cap) FAIL(e, "batch exceeds max_samples");
     CK(e, cudaSetDevice(e->cfg.device));
-    CK(e, cudaMemcpyAsync(e->stage64, obs, sizeof(double) * n * e->cfg.obs_dim, cudaMemcpyDefault, e->stream));
+    if (copy_in(e, e->stage64, obs, sizeof(double) * n * e->cfg.obs_dim)) return -1;
     launch_f64_to_f32(e->stage64, e->obs + (size_t)row0 * e->cfg.obs_dim, n * e->cfg.obs_dim, e->stream);
-    CK(e, cudaMemcpyAsync(e->stage64, act, sizeof(double) * n * e->cfg.act_dim, cudaMemcpyDefault, e->stream));
+    if (copy_in(e, e->stage64, act, sizeof(double) * n * e->cfg.act_dim)) return -1;
     launch_f64_to_f32(e->stage64, e->act + (size_t)row0 * e->cfg.act_dim, n * e->cfg.act_dim, e->stream);
-    if (rew && which == MJB_BATCH_ROLLOUT) CK(e, cudaMemcpyAsync(e->rew, rew, sizeof(double) * n, cudaMemcpyDefault, e->stream));
+    if (rew && which == MJB_BATCH_ROLLOUT && copy_in(e, e->rew, rew, sizeof(double) * n)) return -1;
     e->launches += 2;
     return finish_upload(e, which, n_paths, len, terminated, n);
 }
 
 int mjb_batch_set_advantages(mjb_engine* e, const double* adv_concat) {
-    CK(e, cudaMemcpyAsync(e->adv, adv_concat, sizeof(double) * e->n_roll, cudaMemcpyDefault, e->stream));
+    if (copy_in(e, e->adv, adv_concat, sizeof(double) * e->n_roll)) return -1;
     e->have_adv = true; e->have_white = false;
     return 0;
 }
 
 int mjb_batch_set_adv_white(mjb_engine* e, const float* adv_white) {
-    CK(e, cudaMemcpyAsync(e->adv_white, adv_white, sizeof(float) * e->n_roll, cudaMemcpyDefault, e->stream));
+    if (copy_in(e, e->adv_white, adv_white, sizeof(float) * e->n_roll)) return -1;
     e->have_white = true;
     return 0;
 }
 
 int mjb_batch_set_baseline(mjb_engine* e, const float* base_concat) {
-    CK(e, cudaMemcpyAsync(e->base, base_concat, sizeof(float) * e->n_roll, cudaMemcpyDefault, e->stream));
+    if (copy_in(e, e->base, base_concat, sizeof(float) * e->n_roll)) return -1;
     return 0;
 }
 
 int mjb_batch_set_returns(mjb_engine* e, const double* ret_concat) {
     if (e->fit_in_flight && mjb_vf_fit_end(e, nullptr)) return -1;       // the fallback fit kernels read the returns in place
-    CK(e, cudaMemcpyAsync(e->ret, ret_concat, sizeof(double) * e->n_roll, cudaMemcpyDefault, e->stream));
+    if (copy_in(e, e->ret, ret_concat, sizeof(double) * e->n_roll)) return -1;
     return 0;
 }
 
@@ -714,6 +731,7 @@ int mjb_compute_advantages(mjb_engine* e, double gamma, double gae_lambda, int u
 }
 
 static int d2any(mjb_engine* e, void* dst, const void* src, size_t bytes) {
+    if (is_host_ptr(dst)) e->d2h_bytes += (long long)bytes;
     CK(e, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
     return 0;
@@ -748,6 +766,7 @@ int mjb_process_paths(mjb_engine* e, mjb_batch_stats* out) {
     e->launches += 1;
     std::vector<double> pr((size_t)std::max(1, e->n_paths));
     CK(e, cudaMemcpyAsync(pr.data(), e->path_ret, sizeof(double) * e->n_paths, cudaMemcpyDeviceToHost, e->stream));
+    e->d2h_bytes += (long long)sizeof(double) * e->n_paths;
     CK(e, cudaStreamSynchronize(e->stream));
     double s = 0, mn = INFINITY, mx = -INFINITY;
     for (int i = 0; i < e->n_paths; ++i) { s += pr[i]; mn = std::min(mn, pr[i]); mx = std::max(mx, pr[i]); }
@@ -798,10 +817,10 @@ int mjb_policy_set_transforms(mjb_engine* e, const float* in_shift, const float*
                               const float* out_scale, int which_old) {
     ParamSet& ps = which_old ? e->pold : e->pnew;
     const size_t O = e->cfg.obs_dim, A = e->cfg.act_dim;
-    if (in_shift) CK(e, cudaMemcpyAsync(ps.in_shift, in_shift, O * sizeof(float), cudaMemcpyDefault, e->stream));
-    if (in_scale) CK(e, cudaMemcpyAsync(ps.in_scale, in_scale, O * sizeof(float), cudaMemcpyDefault, e->stream));
-    if (out_shift) CK(e, cudaMemcpyAsync(ps.out_shift, out_shift, A * sizeof(float), cudaMemcpyDefault, e->stream));
-    if (out_scale) CK(e, cudaMemcpyAsync(ps.out_scale, out_scale, A * sizeof(float), cudaMemcpyDefault, e->stream));
+    if (in_shift && copy_in(e, ps.in_shift, in_shift, O * sizeof(float))) return -1;
+    if (in_scale && copy_in(e, ps.in_scale, in_scale, O * sizeof(float))) return -1;
+    if (out_shift && copy_in(e, ps.out_shift, out_shift, A * sizeof(float))) return -1;
+    if (out_scale && copy_in(e, ps.out_scale, out_scale, A * sizeof(float))) return -1;
     CK(e, cudaStreamSynchronize(e->stream));
     if (in_shift || in_scale) {
         std::vector<float> hs(O), hc(O);
@@ -825,7 +844,7 @@ int mjb_policy_vpg(mjb_engine* e, int include_demo, double demo_lam, float* g_ou
 }
 
 int mjb_policy_fvp(mjb_engine* e, const float* v, float damping, const int32_t* idx, int64_t n_idx, float* out) {
-    CK(e, cudaMemcpyAsync(e->tmpv, v, sizeof(float) * e->d, cudaMemcpyDefault, e->stream));
+    if (copy_in(e, e->tmpv, v, sizeof(float) * e->d)) return -1;
     const int* idx_dev = nullptr;
     if (idx) {
         if (upload_idx(e, idx, n_idx)) return -1;
@@ -846,7 +865,7 @@ int mjb_policy_fvp(mjb_engine* e, const float* v, float damping, const int32_t* 
 
 int mjb_policy_cg(mjb_engine* e, const float* b, int iters, float damping, float residual_tol, const int32_t* idx,
                   int64_t n_idx, float* x_out) {
-    if (b) CK(e, cudaMemcpyAsync(e->g, b, sizeof(float) * e->d, cudaMemcpyDefault, e->stream));
+    if (b && copy_in(e, e->g, b, sizeof(float) * e->d)) return -1;
     const int* idx_dev = nullptr;
     if (idx) {
         if (upload_idx(e, idx, (long long)iters * n_idx)) return -1;
@@ -950,9 +969,9 @@ int mjb_vf_dim(const mjb_engine* e) { return e->vf_d; }
 
 int mjb_vf_set_state(mjb_engine* e, const float* w, const float* m, const float* v, int64_t step) {
     if (e->fit_in_flight && mjb_vf_fit_end(e, nullptr)) return -1;
-    if (w) CK(e, cudaMemcpyAsync(e->vf_w, w, sizeof(float) * e->vf_d, cudaMemcpyDefault, e->stream));
-    if (m) CK(e, cudaMemcpyAsync(e->vf_m, m, sizeof(float) * e->vf_d, cudaMemcpyDefault, e->stream));
-    if (v) CK(e, cudaMemcpyAsync(e->vf_v, v, sizeof(float) * e->vf_d, cudaMemcpyDefault, e->stream));
+    if (w && copy_in(e, e->vf_w, w, sizeof(float) * e->vf_d)) return -1;
+    if (m && copy_in(e, e->vf_m, m, sizeof(float) * e->vf_d)) return -1;
+    if (v && copy_in(e, e->vf_v, v, sizeof(float) * e->vf_d)) return -1;
     if (step >= 0) e->vf_step = step;
     launch_prep_mlp(e->vf_w, e->VPL, e->vf_prep, e->stream);
     e->launches += 1;
@@ -1023,20 +1042,17 @@ static int vf_fit_launch(mjb_engine* e, const int32_t* perms, int epochs, int ba
         CK(e, cudaMalloc(&e->perm_dev, sizeof(int) * e->perm_cap));
     }
     // all epochs' permutations go up front (the caller's host buffer is free again when this function returns)
-    CK(e, cudaMemcpyAsync(e->perm_dev, perms, sizeof(int) * (size_t)epochs * N, cudaMemcpyDefault, e->stream));
+    if (copy_in(e, e->perm_dev, perms, sizeof(int) * (size_t)epochs * N)) return -1;
     if (e->comm) NK(e, g_nccl.Broadcast(e->perm_dev, e->perm_dev, (size_t)epochs * N, ncclInt32, 0, e->comm, e->stream));
     VfFitArgs a;
     a.K = e->cfg.obs_dim + 4; a.H1 = e->cfg.vf_hidden[0]; a.H2 = e->cfg.vf_hidden[1]; a.obs_dim = e->cfg.obs_dim;
     a.obs = fobs; a.tstep = ftstep; a.returns = fret; a.n = N;
     a.steps = steps; a.batch = batch_size; a.lr = lr; a.reg = reg_coef; a.beta1 = 0.9f; a.beta2 = 0.999f; a.eps = 1e-8f;
     a.w = e->vf_w; a.m = e->vf_m; a.v = e->vf_v; a.wT = e->vf_wT; a.loss_out = nullptr;
-    // 1 (the default) asks for the tensor-core kernel; shapes it does not cover fall back to the 16-CTA cluster kernels
-    const bool use_tc = e->vf_cluster == 1 && vf_tc_supported(a.K, a.H1, a.H2, a.batch);
-    const int ccl = (e->vf_cluster == 1 && !use_tc) ? 16 : e->vf_cluster;
-    const bool use_mp = !use_tc && ccl > 1 && e->vf_model_parallel && vf_mp_supported(a.K, a.H1, a.H2, a.batch, ccl);
-    const bool use_dp = !use_tc && !use_mp && ccl > 1 && vf_cluster_supported(a.K, a.H1, a.H2, a.batch, ccl);
-    e->vf_sms = (use_mp || use_dp) ? ccl : 1;
-    if (use_mp || use_tc) {
+    // the tensor-core kernel where the shape allows; every other shape runs the single-CTA fp32-FMA kernel
+    const bool use_tc = e->vf_tc_on && vf_tc_supported(a.K, a.H1, a.H2, a.batch);
+    e->vf_sms = 1;
+    if (use_tc) {
         if (N > e->vf_feat_cap) {
             if (e->vf_feat) { cudaFree(e->vf_feat); cudaFree(e->vf_ret32); }
             e->vf_feat_cap = N;
@@ -1051,20 +1067,19 @@ static int vf_fit_launch(mjb_engine* e, const int32_t* perms, int epochs, int ba
             CK(e, cudaMalloc(&e->vf_consts, sizeof(float2) * (size_t)e->vf_consts_cap));
         }
     }
-    if (use_dp && !e->vf_cl_scratch)
-        CK(e, cudaMalloc(&e->vf_cl_scratch, sizeof(float) * vf_cluster_scratch_floats(a.K, a.H1, a.H2, 16)));
     CK(e, cudaStreamSynchronize(e->stream));                 // host permutation buffer consumed; inputs of the fit complete
+    CK(e, cudaEventRecord(e->fit_ev[0], fs));
     for (int ep = 0; ep < epochs; ++ep) {
         a.perm = e->perm_dev + (size_t)ep * N;
         a.step0 = e->vf_step;
         cudaError_t ce;
         if (use_tc) { ce = launch_vf_fit_tc(a, e->vf_feat, e->vf_ret32, e->vf_consts, fs); e->launches += 2; }
-        else if (use_mp) { ce = launch_vf_fit_mp(a, e->vf_feat, e->vf_ret32, e->vf_consts, ccl, fs); e->launches += 2; }
-        else if (use_dp) { ce = launch_vf_fit_cluster(a, e->vf_cl_scratch, ccl, fs); e->launches += 3; }
         else { ce = launch_vf_fit(a, fs); e->launches += 1; }
         if (ce != cudaSuccess) FAIL(e, std::string("vf fit launch (batch<=64, multiple of 4; sizes must fit 220 KB smem): ") + cudaGetErrorString(ce));
         e->vf_step += steps;
     }
+    CK(e, cudaEventRecord(e->fit_ev[1], fs));
+    e->fit_timed = true;
     return 0;
 }
 
@@ -1107,14 +1122,14 @@ int mjb_event_elapsed_ms(mjb_engine* e, int slot_a, int slot_b, float* ms) {
     return 0;
 }
 
-// Developer aid (not part of the public header): per-phase clock64 cycle counters of the cluster fit kernel.
+// Developer aid: per-phase clock64 cycle counters of the tensor-core fit kernel.
 int mjb_dev_vf_profile(mjb_engine* e, long long* out16, int enable) {
     static long long* dev = nullptr;
     if (!dev) { CK(e, cudaMalloc(&dev, 16 * sizeof(long long))); }
-    if (enable) { CK(e, cudaMemset(dev, 0, 16 * sizeof(long long))); vf_cluster_set_prof(dev); vf_mp_set_prof(dev); vf_tc_set_prof(dev); return 0; }
+    if (enable) { CK(e, cudaMemset(dev, 0, 16 * sizeof(long long))); vf_tc_set_prof(dev); return 0; }
     CK(e, cudaStreamSynchronize(e->stream));
     CK(e, cudaMemcpy(out16, dev, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
-    vf_cluster_set_prof(nullptr); vf_mp_set_prof(nullptr); vf_tc_set_prof(nullptr);
+    vf_tc_set_prof(nullptr);
     return 0;
 }
 
@@ -1134,14 +1149,23 @@ int mjb_policy_set_tensor_cores(mjb_engine* e, int on) {
     return (e->tc_ok || !on) ? 0 : 1;       // 1: requested but this shape runs on the fp32 FMA kernels
 }
 
-int mjb_vf_set_cluster(mjb_engine* e, int cluster_ctas, int model_parallel) {
-    if (cluster_ctas != 0 && cluster_ctas != 1 && cluster_ctas != 8 && cluster_ctas != 16)
-        FAIL(e, "cluster size must be 0 (single-CTA FMA), 1 (single-CTA tensor cores), 8 or 16");
-    e->vf_cluster = cluster_ctas;
-    e->vf_model_parallel = model_parallel != 0;
+int mjb_vf_set_tensor_cores(mjb_engine* e, int on) {
+    e->vf_tc_on = on != 0;
     return 0;
 }
 int64_t mjb_kernel_launches(const mjb_engine* e) { return e->launches; }
+int mjb_transfer_stats(const mjb_engine* e, mjb_transfer_stats_t* out) {
+    out->h2d_bytes = e->h2d_bytes; out->d2h_bytes = e->d2h_bytes; out->uploads = e->uploads;
+    return 0;
+}
 int mjb_fvp_timing(mjb_engine* e, float* last_ms) { *last_ms = e->last_fvp_ms; return 0; }
+int mjb_vf_fit_timing(mjb_engine* e, float* last_ms) {
+    *last_ms = 0.f;
+    if (!e->fit_timed) return 0;
+    if (e->fit_in_flight && mjb_vf_fit_end(e, nullptr)) return -1;
+    CK(e, cudaEventSynchronize(e->fit_ev[1]));
+    CK(e, cudaEventElapsedTime(last_ms, e->fit_ev[0], e->fit_ev[1]));
+    return 0;
+}
 
 }  // extern "C"

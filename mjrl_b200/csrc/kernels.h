@@ -115,17 +115,9 @@ struct VfFitArgs {
     float* loss_out;                  // [steps] (optional)
 };
 cudaError_t launch_vf_fit(const VfFitArgs& a, cudaStream_t s);
-// vf_fit_cluster.cu : same chain on a thread-block cluster (minibatch split over C CTAs)
-size_t vf_cluster_scratch_floats(int K, int H1, int H2, int C);
-bool vf_cluster_supported(int K, int H1, int H2, int batch, int C);
-void vf_cluster_set_prof(long long* dev16);
-cudaError_t launch_vf_fit_cluster(const VfFitArgs& a, float* scratch, int C, cudaStream_t s);
-// vf_fit_mp.cu : same chain, hidden units split over the cluster (weights / Adam state stay put, DSMEM exchange)
-bool vf_mp_supported(int K, int H1, int H2, int batch, int C);
-void vf_mp_set_prof(long long* dev16);
+// vf_fit_tc.cu : fp32 feature matrix + targets of the whole batch (built once per fit)
 cudaError_t vf_build_features(const VfFitArgs& a, float* feat, float* ret32, cudaStream_t s);
 // consts: caller-owned scratch of >= a.steps float2 (per-step Adam bias-correction constants, filled by the launcher)
-cudaError_t launch_vf_fit_mp(const VfFitArgs& a, const float* feat, const float* ret32, float2* consts, int C, cudaStream_t s);
 // vf_fit_tc.cu : same chain on one SM with tcgen05 (units on the M axis, Adam moments of W2 in TMEM)
 bool vf_tc_supported(int K, int H1, int H2, int batch);
 void vf_tc_set_prof(long long* dev16);

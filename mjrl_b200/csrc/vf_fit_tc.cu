@@ -1,8 +1,8 @@
 // MLPBaseline.fit on ONE SM with tcgen05 tensor cores (baselines/mlp_baseline.py:61-95, utils/optimize_model.py:7-36).
 //
-// The minibatch-Adam chain is sequential, so the step time is latency.  The cluster kernel (vf_fit_mp.cu) splits the
-// hidden units over 16 SMs and pays three distributed-shared-memory hand-offs per step; this kernel keeps the whole
-// (obs+4) -> 128 -> 128 -> 1 network, its gradients and its optimizer state on one SM and runs the five GEMMs of a
+// The minibatch-Adam chain is sequential, so the step time is latency.  Splitting the hidden units over a thread-block
+// cluster costs three distributed-shared-memory hand-offs per step (measured slower in round 1); this kernel keeps the
+// whole (obs+4) -> 128 -> 128 -> 1 network, its gradients and its optimizer state on one SM and runs the five GEMMs of a
 // step as tcgen05.mma with the HIDDEN UNITS on the M axis (M = 128 is the full-rate shape; the 64-row minibatch is N):
 //
 //   z1^T  [u][n] = W1 [u][k]  x   [n][k]        A = W1  (K-major)   B = X    (K-major)
@@ -560,7 +560,37 @@ __global__ void tc_adam_consts_kernel(float2* out, int steps, long long step0, f
 
 long long* g_tc_prof = nullptr;
 
+// fp32 feature matrix of the whole batch, in the reference's dtypes (mlp_baseline.py:36-58): fp64 feature map, then
+// .astype(float32); built once per fit, all epochs gather minibatch rows from it.
+__global__ void vf_features_kernel(const float* __restrict__ obs, const int* __restrict__ tstep,
+                                   const double* __restrict__ returns, long long n, int obs_dim, int K,
+                                   float* __restrict__ feat, float* __restrict__ ret32) {
+    const long long total = n * K;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / K;
+        const int k = (int)(i - r * K);
+        float val;
+        if (k < obs_dim) {
+            double x = (double)obs[r * obs_dim + k];
+            x = fmin(fmax(x, -10.0), 10.0) / 10.0;
+            val = (float)x;
+        } else {
+            const double tau = (double)tstep[r] / 1000.0;
+            double p = tau;
+            for (int q = obs_dim; q < k; ++q) p *= tau;
+            val = (float)p;
+        }
+        feat[i] = val;
+        if (k == 0) ret32[r] = (float)returns[r];
+    }
+}
+
 }  // namespace
+
+cudaError_t vf_build_features(const VfFitArgs& v, float* feat, float* ret32, cudaStream_t s) {
+    vf_features_kernel<<<148 * 8, 256, 0, s>>>(v.obs, v.tstep, v.returns, v.n, v.obs_dim, v.K, feat, ret32);
+    return cudaGetLastError();
+}
 
 void vf_tc_set_prof(long long* dev16) { g_tc_prof = dev16; }
 

@@ -45,18 +45,34 @@ class Engine:
         h = C.c_void_p()
         if self.lib.mjb_create(C.byref(cfg), C.byref(h)) != 0:
             raise MjbError("mjb_create: " + self.lib.mjb_last_error(None).decode())
-        self.h = h
+        self._h = h
         self.d = self.lib.mjb_policy_dim(h)
         self.vf_d = self.lib.mjb_vf_dim(h)
         self.n = 0
         self.n_demo = 0
-        self._keep = None
+        # residency bookkeeping of the Python mirror (runtime.session / BatchREINFORCE._flat_batch)
+        self.generation = 0            # bumped by every rollout upload
+        self.session_paths = None      # the list object pinned by runtime.session (strong reference, compared with `is`)
+        self.have_returns = False      # device returns valid for the resident batch
+        self.adv_on_device = False     # device advantages were computed by the engine for the resident batch
 
     # ------------------------------------------------------------------ plumbing
+    @property
+    def h(self):
+        """The C handle; a closed engine fails loudly instead of passing NULL into the C ABI."""
+        if self._h is None:
+            raise MjbError("this Engine was closed (runtime.get_engine replaced it with a larger one); "
+                           "re-resolve it through runtime.get_engine")
+        return self._h
+
+    @property
+    def closed(self):
+        return self._h is None
+
     def close(self):
-        if getattr(self, "h", None):
-            self.lib.mjb_destroy(self.h)
-            self.h = None
+        if getattr(self, "_h", None):
+            self.lib.mjb_destroy(self._h)
+            self._h = None
 
     def __del__(self):
         try:
@@ -98,11 +114,17 @@ class Engine:
         term = np.array([bool(p.get("terminated", False)) for p in paths], dtype=np.uint8)
         self._ck(self.lib.mjb_batch_upload(self.h, which, n_paths, ptrs[0], ptrs[1], ptrs[2], _ptr(lens), _ptr(term)),
                  "batch_upload")
+        self._uploaded(which, lens)
+        return self.n
+
+    def _uploaded(self, which, lens):
         if which == ROLLOUT:
             self.n, self.n_demo, self.lens = int(lens.sum()), 0, lens
+            self.generation += 1
+            self.have_returns = False
+            self.adv_on_device = False
         else:
             self.n_demo = int(lens.sum())
-        return self.n
 
     def upload_flat(self, obs, act, rew, lens, terminated, which=ROLLOUT):
         obs = np.ascontiguousarray(obs, dtype=np.float64)
@@ -112,16 +134,14 @@ class Engine:
         term = np.ascontiguousarray(terminated, dtype=np.uint8)
         self._ck(self.lib.mjb_batch_upload_flat(self.h, which, len(lens), _ptr(obs), _ptr(act), _ptr(rew), _ptr(lens),
                                                 _ptr(term)), "batch_upload_flat")
-        if which == ROLLOUT:
-            self.n, self.n_demo, self.lens = int(lens.sum()), 0, lens
-        else:
-            self.n_demo = int(lens.sum())
+        self._uploaded(which, lens)
         return self.n
 
     def set_advantages(self, adv_concat):
         a = np.ascontiguousarray(adv_concat, dtype=np.float64)
         assert a.shape[0] == self.n
         self._ck(self.lib.mjb_batch_set_advantages(self.h, _ptr(a)), "set_advantages")
+        self.adv_on_device = False
 
     def set_white(self, adv_white):
         w = _f32(adv_white)
@@ -132,6 +152,7 @@ class Engine:
         r = np.ascontiguousarray(ret_concat, dtype=np.float64)
         assert r.shape[0] == self.n
         self._ck(self.lib.mjb_batch_set_returns(self.h, _ptr(r)), "set_returns")
+        self.have_returns = True
 
     def n_global(self):
         return int(self.lib.mjb_batch_size(self.h, 2))
@@ -144,6 +165,7 @@ class Engine:
     # ------------------------------------------------------------------ returns / advantages
     def compute_returns(self, gamma):
         self._ck(self.lib.mjb_compute_returns(self.h, float(gamma)), "compute_returns")
+        self.have_returns = True
 
     def vf_predict(self, prefit=False):
         """prefit=True: predictions with the baseline of the last completed fit, without joining a fit in flight."""
@@ -156,6 +178,7 @@ class Engine:
         use_gae = gae_lambda is not None and 0.0 <= gae_lambda <= 1.0
         self._ck(self.lib.mjb_compute_advantages(self.h, float(gamma), float(gae_lambda) if use_gae else 0.0,
                                                  int(use_gae)), "compute_advantages")
+        self.adv_on_device = True
 
     def _get(self, fn, dtype):
         out = np.empty(self.n, dtype=dtype)
@@ -275,8 +298,9 @@ class Engine:
         self._ck(self.lib.mjb_vf_fit_end(self.h, C.byref(err) if return_errors else None), "vf_fit_end")
         return err.value if return_errors else None
 
-    def vf_set_cluster(self, ctas, model_parallel=True):
-        self._ck(self.lib.mjb_vf_set_cluster(self.h, int(ctas), int(model_parallel)), "vf_set_cluster")
+    def vf_set_tensor_cores(self, on=True):
+        """on: the single-SM tcgen05 fit kernel where the shape allows (default); off: the fp32-FMA kernel."""
+        self._ck(self.lib.mjb_vf_set_tensor_cores(self.h, int(on)), "vf_set_tensor_cores")
 
     # ------------------------------------------------------------------ introspection
     def event_record(self, slot):
@@ -289,6 +313,18 @@ class Engine:
 
     def kernel_launches(self):
         return int(self.lib.mjb_kernel_launches(self.h))
+
+    def transfer_stats(self):
+        """(h2d_bytes, d2h_bytes, uploads) issued by this engine so far -- counters kept by the library."""
+        st = _native.TransferStats()
+        self._ck(self.lib.mjb_transfer_stats(self.h, C.byref(st)), "transfer_stats")
+        return int(st.h2d_bytes), int(st.d2h_bytes), int(st.uploads)
+
+    def last_fit_ms(self):
+        """CUDA-event time of the sequential Adam kernels of the last fit (joins a fit in flight)."""
+        t = C.c_float()
+        self._ck(self.lib.mjb_vf_fit_timing(self.h, C.byref(t)), "vf_fit_timing")
+        return float(t.value)
 
     def last_fvp_ms(self):
         t = C.c_float()

@@ -12,6 +12,8 @@ def shard_bounds(path_lengths, world_size):
     n = len(lens)
     if world_size <= 1:
         return [(0, n)]
+    if n < world_size:                      # fewer paths than ranks: one path each, the last ranks stay empty
+        return [(min(r, n), min(r + 1, n)) for r in range(world_size)]
     cum = np.concatenate([[0], np.cumsum(lens)])
     total = cum[-1]
     cuts = [0]

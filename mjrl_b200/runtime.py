@@ -49,7 +49,6 @@ def get_engine(obs_dim, act_dim, hidden=None, vf_hidden=(128, 128), min_log_std=
         eng = Engine(key[0], key[1], key[2], key[3], key[4], max_samples=cap, max_paths=pcap, device=device,
                      world_size=world, rank=rank)
         eng.init_comm()
-        eng.resident = None
         if state is not None:
             eng.set_params(state[0], True, False)
             eng.set_params(state[1], False, True)
@@ -78,21 +77,33 @@ def global_permutation(n):
     return out
 
 
-def fingerprint(paths):
-    if len(paths) == 0:
-        return None
-    a, b = paths[0], paths[-1]
-    return (id(paths), len(paths), id(a["observations"]), id(b["observations"]), len(b["observations"]))
+class session:
+    """`with runtime.session(eng, paths):` uploads `paths` ONCE (always -- the reference reads the arrays it is handed,
+    so a new call never trusts what a previous call left on the device) and pins that list object as the engine's
+    rollout batch for the duration of the block: nested helpers that receive the same list (`returns_on`,
+    `advantages_on`, `fit_begin`, `process_paths`, `train_from_paths`) then skip their own upload.  The pin is a strong
+    reference compared with `is`, never an id(), and it is dropped when the block exits."""
+
+    def __init__(self, eng, paths):
+        self.eng, self.paths = eng, paths
+
+    def __enter__(self):
+        self.eng.upload_paths(self.paths)
+        self.eng.session_paths = self.paths
+        return self.eng
+
+    def __exit__(self, *exc):
+        self.eng.session_paths = None
+        return False
 
 
 def ensure_resident(eng, paths, force=False):
-    """Upload `paths` unless exactly this list is already the engine's rollout batch."""
-    fp = fingerprint(paths)
-    if force or getattr(eng, "resident", None) != fp:
+    """Make `paths` the engine's rollout batch.  Outside a `session` this always uploads; inside one it uploads only
+    when `paths` is not the pinned list (or when forced)."""
+    if force or getattr(eng, "session_paths", None) is not paths:
         eng.upload_paths(paths)
-        eng.resident = fp
-        eng.have_returns = False
-        eng.adv_paths = None
+        if getattr(eng, "session_paths", None) is not None:
+            eng.session_paths = None          # another batch replaced the pinned one: the pin no longer holds
     return eng
 
 

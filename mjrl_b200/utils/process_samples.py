@@ -34,7 +34,6 @@ def compute_returns(paths, gamma):
 def returns_on(eng, paths, gamma, write_back=True):
     runtime.ensure_resident(eng, paths)
     eng.compute_returns(gamma)
-    eng.have_returns = True
     if write_back:
         _scatter(paths, "returns", eng.returns())
 
@@ -53,12 +52,11 @@ def advantages_on(eng, paths, baseline, gamma, gae_lambda=None, normalize=False,
     """fit_in_flight: this step's baseline fit was already launched (it only needs the returns); the advantages use the
     pre-fit baseline exactly as the reference's program order does (batch_reinforce.py:98 before :108)."""
     runtime.ensure_resident(eng, paths)
-    if not getattr(eng, "have_returns", False):
+    if not eng.have_returns:
         if "returns" in paths[0]:
             eng.set_returns(np.concatenate([p["returns"] for p in paths]))
         else:
             eng.compute_returns(gamma)
-        eng.have_returns = True
     if hasattr(baseline, "_eng"):
         if not fit_in_flight:
             baseline._bind(eng)
@@ -73,7 +71,7 @@ def advantages_on(eng, paths, baseline, gamma, gae_lambda=None, normalize=False,
     if normalize:                                      # process_samples.py:14-19,30-35 (unused by the agents)
         adv = (adv - adv.mean()) / (adv.std() + 1e-8)
         eng.set_advantages(adv)
-    eng.adv_paths = runtime.fingerprint(paths)
+        eng.adv_on_device = True       # what the device holds IS what the path dicts receive below
     _scatter(paths, "baseline", base)
     _scatter(paths, "advantages", adv)
 

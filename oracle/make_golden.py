@@ -162,6 +162,44 @@ def run_case(R, name, cfg):
     return out
 
 
+def run_inorm_case(R, cfg, alpha=0.7):
+    """input_normalization (npg_cg.py:101-107): the reference blends the observation moments into
+    policy.model ONLY -- old_model keeps its stale transforms, so LR != 1 and mu_new != mu_old at theta_new = theta_old.
+    Every array is an output of the unmodified reference on the swim_40x250 trajectories."""
+    out = {}
+    spec_env = R.EnvSpec(cfg["obs_dim"], cfg["act_dim"], cfg["horizon"])
+    paths = O.synthetic_paths(cfg["obs_dim"], cfg["act_dim"], cfg["n_paths"], cfg["horizon"], seed=0, ragged=cfg["ragged"])
+    policy = make_policy(R, cfg, spec_env)
+    torch.manual_seed(11)
+    baseline = R.MLPBaseline(spec_env, reg_coef=1e-3, batch_size=64, epochs=2, learn_rate=1e-3)
+    R.process_samples.compute_returns(paths, GAMMA)
+    R.process_samples.compute_advantages(paths, baseline, GAMMA, LAM)
+    agent = R.NPG(None, policy, baseline, normalized_step_size=0.05, seed=123, input_normalization=alpha,
+                  FIM_invert_args={"iters": CG_ITERS, "damping": DAMPING}, save_logs=True)
+    agent.logger = _Log()
+    out["theta0"] = policy.get_param_values()
+    agent.train_from_paths(paths)
+    m, om = policy.model, policy.old_model
+    for k in ("in_shift", "in_scale", "out_shift", "out_scale"):
+        out["new_" + k] = getattr(m, k).data.numpy().copy()
+        out["old_" + k] = getattr(om, k).data.numpy().copy()
+    out["theta1"] = policy.get_param_values()
+    for k in ("alpha", "delta", "kl_dist", "surr_improvement"):
+        out["npg_" + k] = np.float64(agent.logger.kv[k])
+    # the pieces, re-evaluated at theta0 with the blended (new) / stale (old) transforms
+    policy.set_param_values(out["theta0"], set_new=True, set_old=True)
+    obs, act, adv, _, _ = agent.process_paths(paths)
+    out["surr"] = agent.CPI_surrogate(obs, act, adv).data.numpy().ravel()[0]
+    out["kl"] = agent.kl_old_new(obs, act).data.numpy().ravel()[0]
+    out["vpg"] = agent.flat_vpg(obs, act, adv)
+    v = np.random.RandomState(1).randn(policy.d).astype(np.float32)
+    out["fvp_vec"] = v
+    out["fvp_out"] = agent.HVP(obs, act, v, DAMPING)
+    out["meta"] = np.array(repr(dict(cfg, gamma=GAMMA, lam=LAM, damping=DAMPING, cg_iters=CG_ITERS, policy_seed=POLICY_SEED,
+                                     baseline_seed=11, path_seed=0, npg_step=0.05, input_normalization=alpha)))
+    return out
+
+
 class _Log:
     def __init__(self):
         self.kv = {}
@@ -211,6 +249,7 @@ def main():
     R = ref_shim.load()
     torch.set_num_threads(1)          # bitwise-repeatable reference outputs
     np.savez_compressed(os.path.join(GOLDEN_DIR, "kat.npz"), **kat())
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "inorm_swim_40x250.npz"), **run_inorm_case(R, CASES["swim_40x250"]))
     for name, cfg in CASES.items():
         out = run_case(R, name, cfg)
         path = os.path.join(GOLDEN_DIR, name + ".npz")

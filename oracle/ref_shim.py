@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE ONLY -- import the real aravindr93/mjrl reference on CPU.
 
-Only usable where a reference checkout exists ($MJRL_REF or /root/reference, i.e. the
-build container; the GPU box has none).  Used by oracle/make_golden.py to generate the
+Usable where a reference checkout exists: $MJRL_REF, /root/reference (the build container) or
+baseline/_ref (the offline `pip install --target` of the unmodified reference, git-ignored, which
+travels to the GPU box with the snapshot; written by __graft_entry__.build()).  Used by oracle/make_golden.py to generate the
 committed fixtures in tests/golden/ and by tests/test_oracle_vs_reference.py to pin the
 restatement in oracle/npg_oracle.py against the reference itself.
 
@@ -18,7 +19,8 @@ import types
 
 
 def reference_root():
-    for cand in (os.environ.get("MJRL_REF"), "/root/reference"):
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cand in (os.environ.get("MJRL_REF"), "/root/reference", os.path.join(here, "baseline", "_ref")):
         if cand and os.path.isdir(os.path.join(cand, "mjrl", "algos")):
             return cand
     return None
@@ -38,7 +40,7 @@ def load():
         return _loaded
     root = reference_root()
     if root is None:
-        raise RuntimeError("mjrl reference checkout not found ($MJRL_REF or /root/reference)")
+        raise RuntimeError("mjrl reference not found ($MJRL_REF, /root/reference or baseline/_ref)")
     if "mjrl" in sys.modules and not getattr(sys.modules["mjrl"], "_b200_shim", False):
         raise RuntimeError("a real `mjrl` package is already imported; cannot shim")
     pkg = types.ModuleType("mjrl")

@@ -24,6 +24,11 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert getattr(lib, name) is not None
     assert lib.mjb_version() == 1
+    # the dynamic symbol table of the .so itself: exactly the declared entry points carry the mjb_ prefix
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", _native.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = sorted({ln.split()[-1] for ln in out.splitlines() if ln.split() and ln.split()[-1].startswith("mjb_")})
+    assert exported == declared, (set(exported) ^ set(declared))
 
 
 def test_header_cites_reference():

@@ -145,15 +145,15 @@ def test_policy_steps(case, cuda_device):
     eng.close()
 
 
-@pytest.mark.parametrize("cluster", [(1, True), (16, True), (8, True), (8, False), (16, False), (0, False)])
-@pytest.mark.parametrize("case", ["pm_5x50", "pm_40x25_ragged", "swim_40x250", "linear_30x200"])
-def test_baseline_fit(case, cluster, cuda_device):
-    """cluster = (CTAs of the thread-block cluster running the sequential Adam chain, model-parallel?);
-    1 CTA = the single-SM tensor-core kernel (the default), 0 CTAs = single-CTA fp32-FMA kernel.  linear_30x200 (44 input features) exercises the fallbacks of the cluster kernels."""
+@pytest.mark.parametrize("tensor_cores", [True, False])
+@pytest.mark.parametrize("case", ["pm_5x50", "pm_40x25_ragged", "swim_40x250", "cheetah_24x500", "linear_30x200"])
+def test_baseline_fit(case, tensor_cores, cuda_device):
+    """tensor_cores: the single-SM tcgen05 kernel (the default) / the single-CTA fp32-FMA kernel.  linear_30x200
+    has 44 input features and cheetah_24x500 21: both widths of the tensor-core kernel's layer-1 K range."""
     g = load_golden(case)
     paths = golden_paths(g)
     eng = make_engine(g, cuda_device)
-    eng.vf_set_cluster(*cluster)
+    eng.vf_set_tensor_cores(tensor_cores)
     eng.upload_paths(paths)
     eng.compute_returns(g["meta"]["gamma"])
     err = eng.vf_fit(g["fit_perms"][:2], 64, 1e-3, 1e-3, return_errors=True)

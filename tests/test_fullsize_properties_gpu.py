@@ -112,11 +112,4 @@ def test_fullsize_fit_properties(cuda_device):
     eng.vf_fit(perm, 64, 1e-3, 1e-3)
     w2 = eng.vf_get_state()[0]
     assert np.array_equal(w1, w2)
-    # the fp32 cluster kernel reaches the same fit quality from the same state (the chains decorrelate in the
-    # weights after ~1e4 chaotic steps, so compare the error, not the parameters)
-    eng.vf_set_state(w0, m0, v0, s0)
-    eng.vf_set_cluster(16, True)
-    e0c, e1c = eng.vf_fit(perm, 64, 1e-3, 1e-3, return_errors=True)
-    assert abs(e0c - e0) <= 1e-6 * abs(e0)
-    assert abs(e1c - e1) <= 0.05 * abs(e1)
     eng.close()
