@@ -31,8 +31,10 @@ class BatchREINFORCE:
         vf_hidden = getattr(self.baseline, "hidden_sizes", (128, 128)) if hasattr(self.baseline, "_eng") else (128, 128)
         eng = runtime.get_engine(pol.n, pol.m, pol.hidden_sizes, vf_hidden, float(pol.min_log_std),
                                  need_samples=need_samples, need_paths=need_paths)
-        if eng is not self._engine:
+        if eng is not self._engine or getattr(eng, "policy_owner", None) is not self:
+            # a different engine, or another agent pushed ITS policy into this engine since: push again
             self._engine, self._pushed = eng, None
+            eng.policy_owner = self
         if hasattr(self.baseline, "_bind"):
             self.baseline._bind(eng)
         return eng
@@ -165,7 +167,11 @@ class BatchREINFORCE:
         if self.save_logs:
             self.logger.log_kv('num_samples', int(np.sum([p["rewards"].shape[0] for p in paths])))
         ts = timer.time()
-        if overlap:
+        if overlap and not self.save_logs and hasattr(self.baseline, "fit_defer"):
+            # theta is back on the host: return now.  The fit keeps running on its own stream and is joined by whoever
+            # reads the baseline next (predict / fit / pickling), so the next batch's upload overlaps its tail.
+            self.baseline.fit_defer()
+        elif overlap:
             error_after = self.baseline.fit_end(return_errors=self.save_logs)
         elif self.save_logs:
             error_before, error_after = self.baseline.fit(paths, return_errors=True)

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/mjrl_b200.h"
@@ -67,6 +68,7 @@ struct mjb_engine {
     cudaStream_t stream = nullptr;
     cudaStream_t stream_vf = nullptr;      // side stream of the asynchronous baseline fit
     bool fit_in_flight = false;
+    bool fit_reads_batch = false;          // the fit in flight reads obs / tstep / returns in place (FMA fallback kernel)
     std::string err;
     long long launches = 0;
     long long h2d_bytes = 0, d2h_bytes = 0, uploads = 0;   // host<->device traffic actually issued (mjb_transfer_stats)
@@ -124,6 +126,15 @@ struct mjb_engine {
     cudaEvent_t fvp_ev[kFvpRing][2];
     long long fvp_count = 0;
     float last_fvp_ms = 0.f;
+    // ---- CUDA graphs of the device-resident CG loop (one per distinct launch shape)
+    struct CgGraph {
+        long long n = 0; const int* idx = nullptr; long long n_idx = 0; int iters = 0; float damping = 0.f, tol = 0.f;
+        int sms = 0; bool tc = false; cudaGraphExec_t exec = nullptr;
+        std::vector<cudaEvent_t> ev;              // 2 per iteration: around the FVP tile kernel
+    };
+    std::vector<CgGraph> cg_graphs;
+    bool graphs_on = true;
+    const CgGraph* last_cg_graph = nullptr;       // set when the last CG ran as a graph (its events time the FVP launches)
     cudaEvent_t fit_ev[2] = {nullptr, nullptr};     // around the sequential Adam kernels of the last fit (on its stream)
     bool fit_timed = false;
 };
@@ -267,47 +278,49 @@ int ensure_old_cache(mjb_engine* e, long long rows) {
 }
 
 // F v (undamped, all-reduced) into out.  v, out: device pointers of d floats.
-int fvp_device(mjb_engine* e, const float* v, const int* idx, long long n_idx, float* out) {
+// have_vscale: e->tc_vscale already holds the power-of-two scale of v (written by cg_init / cg_update).
+// ev0/ev1: events recorded around the tile kernel (the FVP ring slot, or a graph's own pair while capturing).
+int fvp_device(mjb_engine* e, const float* v, const int* idx, long long n_idx, float* out, bool have_vscale = false,
+               cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr) {
     const long long n = idx ? n_idx : e->n_roll;
+    if (!ev0) {
+        const int slot = (int)(e->fvp_count % mjb_engine::kFvpRing);
+        ev0 = e->fvp_ev[slot][0]; ev1 = e->fvp_ev[slot][1];
+        e->fvp_count += 1;
+    }
     if (e->tc_ok && e->tc_on) {
         // tensor-core path: scale v to O(1) (exact power of two), split to fp16 hi/lo, tcgen05 tile kernel
-        launch_tc_vscale(v, e->d, e->tc_vscale, e->stream);
+        if (!have_vscale) { launch_tc_vscale(v, e->d, e->tc_vscale, e->stream); e->launches += 1; }
         if (e->linear) launch_lin_tc_prep(v, e->cfg.obs_dim, e->A, e->tc_vscale, e->tc_prep_tan, e->stream);
         else launch_tc_prep(v, e->PL, e->tc_vscale, e->tc_prep_tan, e->stream);
         const int sms = e->num_sms - (e->fit_in_flight ? e->vf_sms : 0);
         const int tile_rows = e->linear ? 64 : 128;
         const long long tiles = (n + tile_rows - 1) / tile_rows;
         const int grid = (int)std::max<long long>(1, std::min<long long>(tiles, sms));
-        CK(e, cudaMemsetAsync(e->gpartial, 0, sizeof(float) * (size_t)grid * e->gstride, e->stream));
-        const int slot = (int)(e->fvp_count % mjb_engine::kFvpRing);
-        cudaEventRecord(e->fvp_ev[slot][0], e->stream);
+        CK(e, cudaEventRecord(ev0, e->stream));                 // (the kernels zero their own gradient partials)
         cudaError_t ce = e->linear
             ? launch_linear_tc(e->tc_prep_tan, e->pnew.theta, e->pnew.in_shift, e->pnew.in_scale, e->pnew.out_scale,
                                e->pnew.in_ident, e->obs, e->cfg.obs_dim, e->A, idx, n, e->gpartial, e->gstride, e->LL.tW, e->LL.tb, e->LL.tLS, grid, e->stream)
             : launch_fvp_tc(e->PL, e->tc_prep_new, e->tc_prep_tan, e->pnew.in_shift, e->pnew.in_scale,
                             e->pnew.out_scale, e->obs, idx, n, e->gpartial, e->gstride, grid, e->stream);
         if (ce != cudaSuccess) FAIL(e, std::string("fvp_tc launch: ") + cudaGetErrorString(ce));
-        cudaEventRecord(e->fvp_ev[slot][1], e->stream);
-        e->fvp_count += 1;
-        double* sc = e->dsc + DS_TCSCALE;
-        launch_tc_scale_fix(e->dsc + (idx ? DS_SCALE_SUB : DS_SCALE), e->tc_vscale, sc, e->stream);
-        launch_reduce_partials(e->gpartial, grid, e->gstride, e->d, sc, out, e->pnew.theta, v, e->tLS, 1, e->stream);
-        e->launches += 5;
+        CK(e, cudaEventRecord(ev1, e->stream));
+        launch_reduce_partials(e->gpartial, grid, e->gstride, e->d, e->dsc + (idx ? DS_SCALE_SUB : DS_SCALE), out,
+                               e->pnew.theta, v, e->tLS, 1, e->tc_vscale, e->stream);
+        e->launches += 3;
         CK(e, cudaGetLastError());
         return allreduce(e, out, e->d, ncclFloat);
     }
     if (e->linear) launch_prep_linear(v, e->LL, e->prep_tan, e->stream);
     else launch_prep_mlp(v, e->PL, e->prep_tan, e->stream);
     e->launches += 1;
-    const int slot = (int)(e->fvp_count % mjb_engine::kFvpRing);
     // the memset of the gradient partials belongs to the FVP; the event pair brackets memset + tile kernel
-    cudaEventRecord(e->fvp_ev[slot][0], e->stream);
+    CK(e, cudaEventRecord(ev0, e->stream));
     int grid = run_policy(e, MODE_FVP, e->pnew, e->prep_tan, n, idx, nullptr, 0);
     if (grid < 0) return -1;
-    cudaEventRecord(e->fvp_ev[slot][1], e->stream);
-    e->fvp_count += 1;
+    CK(e, cudaEventRecord(ev1, e->stream));
     launch_reduce_partials(e->gpartial, grid, e->gstride, e->d, e->dsc + (idx ? DS_SCALE_SUB : DS_SCALE), out,
-                           e->pnew.theta, v, e->tLS, 1, e->stream);
+                           e->pnew.theta, v, e->tLS, 1, nullptr, e->stream);
     e->launches += 1;
     CK(e, cudaGetLastError());
     return allreduce(e, out, e->d, ncclFloat);
@@ -362,7 +375,7 @@ int vpg_device(mjb_engine* e, int include_demo, double demo_lam, double* surr) {
     int grid = run_policy(e, MODE_VPG, e->pnew, nullptr, n, nullptr, w, flags);
     if (grid < 0) return -1;
     if (flags == OLD_WRITE) { e->old_cache_valid = true; e->cache_rows = n; }
-    launch_reduce_partials(e->gpartial, grid, e->gstride, e->d, e->dsc + DS_SCALE, e->g, nullptr, nullptr, e->tLS, 0, e->stream);
+    launch_reduce_partials(e->gpartial, grid, e->gstride, e->d, e->dsc + DS_SCALE, e->g, nullptr, nullptr, e->tLS, 0, nullptr, e->stream);
     e->launches += 1;
     if (allreduce(e, e->g, e->d, ncclFloat)) return -1;
     if (surr) {
@@ -383,16 +396,76 @@ int vpg_device(mjb_engine* e, int include_demo, double demo_lam, double* surr) {
     return 0;
 }
 
-int cg_device(mjb_engine* e, const float* b, int iters, float damping, float tol, const int* idx_dev, long long n_idx) {
-    launch_cg_init(b, e->x, e->r, e->p, e->d, e->dsc + DS_CG, e->stream);
+// The launches of one cg_solve (utils/cg_solve.py:3-22): init, then per iteration {tangent prep, FVP tile kernel,
+// partial reduce, all-reduce, fused update (which also emits the next tangent's scale)}.
+int cg_body(mjb_engine* e, const float* b, int iters, float damping, float tol, const int* idx_dev, long long n_idx,
+            const std::vector<cudaEvent_t>* evs) {
+    const bool tc = e->tc_ok && e->tc_on;
+    launch_cg_init(b, e->x, e->r, e->p, e->d, e->dsc + DS_CG, tc ? e->tc_vscale : nullptr, e->stream);
     e->launches += 1;
     for (int i = 0; i < iters; ++i) {
         const int* idx = idx_dev ? idx_dev + (size_t)i * n_idx : nullptr;
-        if (fvp_device(e, e->p, idx, n_idx, e->Fp)) return -1;
-        launch_cg_update(e->Fp, damping, tol, e->x, e->r, e->p, e->d, e->dsc + DS_CG, e->stream);
+        if (fvp_device(e, e->p, idx, n_idx, e->Fp, tc, evs ? (*evs)[2 * i] : nullptr, evs ? (*evs)[2 * i + 1] : nullptr)) return -1;
+        launch_cg_update(e->Fp, damping, tol, e->x, e->r, e->p, e->d, e->dsc + DS_CG, tc ? e->tc_vscale : nullptr, e->stream);
         e->launches += 1;
     }
     CK(e, cudaGetLastError());
+    return 0;
+}
+
+// cg_solve as ONE graph launch: the loop is launch-bound (d <= 83 k floats per vector op, ~50 nodes), so it is captured
+// once per distinct shape and replayed; anything that prevents the capture falls back to plain stream launches.
+int cg_device(mjb_engine* e, const float* b, int iters, float damping, float tol, const int* idx_dev, long long n_idx) {
+    e->last_cg_graph = nullptr;
+    if (!e->graphs_on || iters < 1) return cg_body(e, b, iters, damping, tol, idx_dev, n_idx, nullptr);
+    const long long n = idx_dev ? n_idx : e->n_roll;
+    const int sms = e->num_sms - (e->fit_in_flight ? e->vf_sms : 0);
+    const bool tc = e->tc_ok && e->tc_on;
+    mjb_engine::CgGraph* hit = nullptr;
+    for (auto& gph : e->cg_graphs)
+        if (gph.n == n && gph.idx == idx_dev && gph.n_idx == n_idx && gph.iters == iters && gph.damping == damping &&
+            gph.tol == tol && gph.sms == sms && gph.tc == tc) { hit = &gph; break; }
+    if (!hit) {
+        if (e->cg_graphs.size() >= 8) {                       // shapes keep changing: drop the oldest
+            auto& old = e->cg_graphs.front();
+            if (old.exec) cudaGraphExecDestroy(old.exec);
+            for (auto& ev : old.ev) if (ev) cudaEventDestroy(ev);
+            e->cg_graphs.erase(e->cg_graphs.begin());
+        }
+        mjb_engine::CgGraph gph;
+        gph.n = n; gph.idx = idx_dev; gph.n_idx = n_idx; gph.iters = iters; gph.damping = damping; gph.tol = tol;
+        gph.sms = sms; gph.tc = tc;
+        gph.ev.assign((size_t)2 * iters, nullptr);
+        for (auto& ev : gph.ev) CK(e, cudaEventCreate(&ev));
+        // occupancy queries / attribute setters of the kernels must not run for the first time inside a capture
+        if (!tc && e->occ[MODE_FVP] == 0) {
+            e->occ[MODE_FVP] = e->linear ? 2 : occupancy_any(e->H, MODE_FVP, e->PL.YR);
+            if (e->occ[MODE_FVP] <= 0) FAIL(e, "kernel does not fit on this device (occupancy 0)");
+        }
+        const long long launches0 = e->launches;
+        cudaGraph_t graph = nullptr;
+        bool ok = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            const int rc = cg_body(e, b, iters, damping, tol, idx_dev, n_idx, &gph.ev);
+            const cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+            ok = rc == 0 && ce == cudaSuccess && graph != nullptr;
+        }
+        if (ok) ok = cudaGraphInstantiate(&gph.exec, graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+        e->launches = launches0;                              // capturing launched nothing
+        if (!ok) {
+            cudaGetLastError();
+            for (auto& ev : gph.ev) if (ev) cudaEventDestroy(ev);
+            e->graphs_on = false;                             // e.g. a collective that cannot be captured: stay eager
+            return cg_body(e, b, iters, damping, tol, idx_dev, n_idx, nullptr);
+        }
+        e->cg_graphs.push_back(std::move(gph));
+        hit = &e->cg_graphs.back();
+    }
+    CK(e, cudaGraphLaunch(hit->exec, e->stream));
+    const bool tcp = tc;
+    e->launches += 1 + (long long)iters * (tcp ? 4 : 5);      // kernels inside the graph (memset nodes not counted)
+    e->last_cg_graph = hit;
     return 0;
 }
 
@@ -429,6 +502,10 @@ void mjb_destroy(mjb_engine* e) {
     for (auto& ev : e->user_ev) if (ev) cudaEventDestroy(ev);
     for (auto& pr : e->fvp_ev) for (auto& ev : pr) if (ev) cudaEventDestroy(ev);
     for (auto& ev : e->fit_ev) if (ev) cudaEventDestroy(ev);
+    for (auto& gph : e->cg_graphs) {
+        if (gph.exec) cudaGraphExecDestroy(gph.exec);
+        for (auto& ev : gph.ev) if (ev) cudaEventDestroy(ev);
+    }
     if (e->stream_vf) { cudaStreamSynchronize(e->stream_vf); cudaStreamDestroy(e->stream_vf); }
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -495,6 +572,7 @@ int mjb_create(const mjb_config* cfg, mjb_engine** out) {
     ALLOC(e->prep_tan, e->prep_total);
     e->tc_ok = e->linear ? lin_tc_supported(cfg->obs_dim, cfg->act_dim) : fvp_tc_supported(e->PL);
     if (const char* env = getenv("MJRL_B200_TC")) e->tc_on = atoi(env) != 0;
+    if (const char* env = getenv("MJRL_B200_GRAPH")) e->graphs_on = atoi(env) != 0;
     if (e->tc_ok) {
         const size_t pb = e->linear ? lin_tc_prep_bytes() : fvp_tc_prep_bytes();
         ALLOC(e->tc_prep_new, pb); ALLOC(e->tc_prep_tan, pb); ALLOC(e->tc_vscale, 2);
@@ -590,47 +668,80 @@ int mjb_batch_upload(mjb_engine* e, int which, int32_t n_paths, const double* co
                      const double* const* rew, const int32_t* len, const uint8_t* terminated) {
     if (which != MJB_BATCH_ROLLOUT && which != MJB_BATCH_DEMO) FAIL(e, "bad batch id");
     if (n_paths < 0 || (which == MJB_BATCH_ROLLOUT && n_paths > e->cfg.max_paths)) FAIL(e, "too many paths for max_paths");
-    // a fit in flight reads the rollout rows (or its own feature copy); demonstration rows live behind them
-    if (which == MJB_BATCH_ROLLOUT && e->fit_in_flight && mjb_vf_fit_end(e, nullptr)) return -1;
+    // The tensor-core fit works on its own fp32 feature / target copies, so the NEXT batch may be uploaded while it is
+    // still running (sampler hand-off overlapped with the previous step's fit); only the FMA fallback kernel reads
+    // the rollout rows in place and has to be joined first.  Demonstration rows live behind the rollout rows.
+    if (which == MJB_BATCH_ROLLOUT && e->fit_in_flight && e->fit_reads_batch && mjb_vf_fit_end(e, nullptr)) return -1;
     long long n = 0;
     for (int i = 0; i < n_paths; ++i) { if (len[i] < 0) FAIL(e, "negative path length"); n += len[i]; }
     const long long row0 = which == MJB_BATCH_DEMO ? e->n_roll : 0;
     if (row0 + n > e->cap) FAIL(e, "batch exceeds max_samples");
     CK(e, cudaSetDevice(e->cfg.device));
-    // stream each field through the double-buffered pinned ring: host memcpy of chunk k overlaps the DMA of k-1
+    // Pack on the fly (samplers/core.py:85-92 path dicts -> batch_reinforce.py:180-182 concat order): each field streams
+    // through a double-buffered pinned ring; a few host threads gather the per-path float64 arrays into the slot --
+    // observations and actions are rounded to fp32 right there (the reference's `.float()`), so half the bytes cross
+    // PCIe and no device-side cast pass is needed -- while the DMA of the previous slot is in flight.
+    std::vector<size_t> pre((size_t)n_paths + 1, 0);
+    for (int i = 0; i < n_paths; ++i) pre[i + 1] = pre[i] + (size_t)len[i];
+    unsigned hw = std::thread::hardware_concurrency();
+    int nthr = (int)std::min<unsigned>(8u, std::max<unsigned>(1u, hw));
+    if (const char* env = getenv("MJRL_B200_UPLOAD_THREADS")) nthr = std::max(1, atoi(env));
     struct Field { const double* const* src; int width; int kind; };
-    const Field fields[3] = {{obs, e->cfg.obs_dim, 0}, {act, e->cfg.act_dim, 1}, {rew, 1, 2}};
-    cudaEvent_t done[2] = {e->ev[0], e->ev[1]};
+    const Field fields[3] = {{rew, 1, 2}, {obs, e->cfg.obs_dim, 0}, {act, e->cfg.act_dim, 1}};
+    cudaEvent_t done[2] = {e->ev[4], e->ev[5]};
     int slot = 0, used[2] = {0, 0};
     for (const Field& f : fields) {
         if (!f.src) continue;
         if (f.kind == 2 && which == MJB_BATCH_DEMO) continue;
-        const size_t cap_el = e->pinned_bytes / sizeof(double);
-        double* dst_dev = (f.kind == 2) ? e->rew : e->stage64;
-        size_t dev_off = 0;
-        int pi = 0; size_t in_path = 0;
-        while (pi < n_paths) {
+        const bool to_f32 = f.kind != 2;
+        const size_t esz = to_f32 ? sizeof(float) : sizeof(double);
+        const size_t cap_el = e->pinned_bytes / esz;
+        const size_t total_el = (size_t)n * f.width;
+        char* dst_dev = f.kind == 2 ? reinterpret_cast<char*>(e->rew)
+                      : f.kind == 0 ? reinterpret_cast<char*>(e->obs + (size_t)row0 * e->cfg.obs_dim)
+                                    : reinterpret_cast<char*>(e->act + (size_t)row0 * e->cfg.act_dim);
+        for (size_t el0 = 0; el0 < total_el; el0 += cap_el) {
+            const size_t el1 = std::min(total_el, el0 + cap_el);
             if (used[slot]) CK(e, cudaEventSynchronize(done[slot]));
-            double* pin = reinterpret_cast<double*>(static_cast<char*>(e->pinned) + slot * e->pinned_bytes);
-            size_t fill = 0;
-            while (pi < n_paths && fill < cap_el) {
-                const size_t total = (size_t)len[pi] * f.width;
-                const size_t take = std::min(total - in_path, cap_el - fill);
-                memcpy(pin + fill, f.src[pi] + in_path, take * sizeof(double));
-                fill += take; in_path += take;
-                if (in_path == total) { ++pi; in_path = 0; }
+            char* pin = static_cast<char*>(e->pinned) + (size_t)slot * e->pinned_bytes;
+            // elements [el0, el1) of the concatenated field, gathered by nthr threads (equal byte ranges)
+            auto work = [&](int t, int T) {
+                const size_t span = el1 - el0;
+                size_t a0 = el0 + span * (size_t)t / (size_t)T, a1 = el0 + span * (size_t)(t + 1) / (size_t)T;
+                // path containing element a0: last i with pre[i] * width <= a0
+                size_t pi = (size_t)(std::upper_bound(pre.begin(), pre.end(), a0 / (size_t)f.width) - pre.begin()) - 1;
+                while (a0 < a1) {
+                    const size_t p_lo = pre[pi] * (size_t)f.width, p_hi = pre[pi + 1] * (size_t)f.width;
+                    const size_t take = std::min(a1, p_hi) - a0;
+                    const double* sp = f.src[pi] + (a0 - p_lo);
+                    if (to_f32) {
+                        float* dp = reinterpret_cast<float*>(pin) + (a0 - el0);
+                        for (size_t k = 0; k < take; ++k) dp[k] = (float)sp[k];
+                    } else {
+                        memcpy(reinterpret_cast<double*>(pin) + (a0 - el0), sp, take * sizeof(double));
+                    }
+                    a0 += take;
+                    if (a0 == p_hi) ++pi;
+                }
+            };
+            const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)nthr, (el1 - el0) / 65536 + 1));
+            if (T == 1) work(0, 1);
+            else {
+                std::vector<std::thread> pool;
+                for (int t = 1; t < T; ++t) pool.emplace_back(work, t, T);
+                work(0, T);
+                for (auto& th : pool) th.join();
             }
-            CK(e, cudaMemcpyAsync(dst_dev + dev_off, pin, fill * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-            e->h2d_bytes += (long long)(fill * sizeof(double));
+            const size_t bytes = (el1 - el0) * esz;
+            CK(e, cudaMemcpyAsync(dst_dev + el0 * esz, pin, bytes, cudaMemcpyHostToDevice, e->stream));
+            e->h2d_bytes += (long long)bytes;
             CK(e, cudaEventRecord(done[slot], e->stream));
             used[slot] = 1;
-            dev_off += fill;
             slot ^= 1;
         }
-        if (f.kind == 0) launch_f64_to_f32(e->stage64, e->obs + (size_t)row0 * e->cfg.obs_dim, n * e->cfg.obs_dim, e->stream);
-        if (f.kind == 1) launch_f64_to_f32(e->stage64, e->act + (size_t)row0 * e->cfg.act_dim, n * e->cfg.act_dim, e->stream);
-        e->launches += (f.kind != 2);
     }
+    // the pinned slots must not be refilled by a later call before these copies have landed
+    for (int sl = 0; sl < 2; ++sl) if (used[sl]) CK(e, cudaEventSynchronize(done[sl]));
     return finish_upload(e, which, n_paths, len, terminated, n);
 }
 
@@ -638,7 +749,7 @@ int mjb_batch_upload_flat(mjb_engine* e, int which, int32_t n_paths, const doubl
                           const double* rew, const int32_t* len, const uint8_t* terminated) {
     if (which != MJB_BATCH_ROLLOUT && which != MJB_BATCH_DEMO) FAIL(e, "bad batch id");
     if (n_paths < 0 || (which == MJB_BATCH_ROLLOUT && n_paths > e->cfg.max_paths)) FAIL(e, "too many paths for max_paths");
-    if (which == MJB_BATCH_ROLLOUT && e->fit_in_flight && mjb_vf_fit_end(e, nullptr)) return -1;
+    if (which == MJB_BATCH_ROLLOUT && e->fit_in_flight && e->fit_reads_batch && mjb_vf_fit_end(e, nullptr)) return -1;
     long long n = 0;
     for (int i = 0; i < n_paths; ++i) n += len[i];
     const long long row0 = which == MJB_BATCH_DEMO ? e->n_roll : 0;
@@ -671,7 +782,7 @@ int mjb_batch_set_baseline(mjb_engine* e, const float* base_concat) {
 }
 
 int mjb_batch_set_returns(mjb_engine* e, const double* ret_concat) {
-    if (e->fit_in_flight && mjb_vf_fit_end(e, nullptr)) return -1;       // the fallback fit kernels read the returns in place
+    if (e->fit_in_flight && e->fit_reads_batch && mjb_vf_fit_end(e, nullptr)) return -1;   // fallback kernel: reads the returns in place
     if (copy_in(e, e->ret, ret_concat, sizeof(double) * e->n_roll)) return -1;
     return 0;
 }
@@ -682,7 +793,7 @@ int64_t mjb_batch_size(const mjb_engine* e, int which) {
 
 // ------------------------------------------------------------------------------- returns / advantages
 int mjb_compute_returns(mjb_engine* e, double gamma) {
-    if (e->fit_in_flight && mjb_vf_fit_end(e, nullptr)) return -1;       // the fallback fit kernels read the returns in place
+    if (e->fit_in_flight && e->fit_reads_batch && mjb_vf_fit_end(e, nullptr)) return -1;   // fallback kernel: reads the returns in place
     launch_returns(e->rew, e->path_off, e->n_paths, gamma, e->ret, e->stream);
     e->launches += 1;
     CK(e, cudaGetLastError());
@@ -946,6 +1057,16 @@ int mjb_policy_step(mjb_engine* e, int algo, double step_size_or_kl, double cons
     cudaEventElapsedTime(&st.time_vpg_ms, e->ev[0], e->ev[1]);
     cudaEventElapsedTime(&st.time_npg_ms, e->ev[1], e->ev[2]);
     cudaEventElapsedTime(&st.time_eval_ms, e->ev[2], e->ev[3]);
+    if (e->last_cg_graph) {
+        const auto& evs = e->last_cg_graph->ev;
+        for (size_t k = 0; k + 1 < evs.size(); k += 2) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, evs[k], evs[k + 1]) != cudaSuccess) { cudaGetLastError(); continue; }
+            st.fvp_kernel_ms_sum += ms;
+            st.fvp_launches += 1;
+            e->last_fvp_ms = ms;
+        }
+    }
     for (long long k = std::max(fvp0, e->fvp_count - mjb_engine::kFvpRing); k < e->fvp_count; ++k) {
         float ms = 0.f;
         const int slot = (int)(k % mjb_engine::kFvpRing);
@@ -1052,6 +1173,7 @@ static int vf_fit_launch(mjb_engine* e, const int32_t* perms, int epochs, int ba
     // the tensor-core kernel where the shape allows; every other shape runs the single-CTA fp32-FMA kernel
     const bool use_tc = e->vf_tc_on && vf_tc_supported(a.K, a.H1, a.H2, a.batch);
     e->vf_sms = 1;
+    e->fit_reads_batch = !use_tc && !e->comm;        // (the replicated multi-GPU fit works on gathered copies)
     if (use_tc) {
         if (N > e->vf_feat_cap) {
             if (e->vf_feat) { cudaFree(e->vf_feat); cudaFree(e->vf_ret32); }

@@ -132,6 +132,10 @@ __global__ void __launch_bounds__(512, 1) fvp_tc_kernel(const TcFvpArgs a) {
         mbar_init(&bars[3], 1); mbar_init(&bars[4], 1);
     }
     for (int i = tid; i < (S_RING - S_PHI) / 16; i += 512) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    {   // this CTA's gradient partial starts at zero (no memset node in front of the kernel); gstride is a multiple of 32
+        float4* gz = reinterpret_cast<float4*>(a.gpartial + (size_t)blockIdx.x * a.gstride);
+        for (int i = tid; i < (int)(a.gstride / 4); i += 512) gz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     __syncthreads();
     if (tid < 128) {                                                 // ones column (feature 128) of P: carries d/db2 through G2
         const __half one = __float2half_rn(1.0f);
@@ -562,11 +566,6 @@ __global__ void tc_vscale_kernel(const float* __restrict__ v, int d, float* out)
     }
 }
 
-__global__ void tc_scale_fix_kernel(const double* in2, const float* vscale, double* out2) {
-    out2[0] = in2[0] * (double)vscale[1];
-    out2[1] = in2[1];
-}
-
 }  // namespace
 
 size_t fvp_tc_prep_bytes() { return (size_t)round_up(G_TOTAL, 256); }
@@ -579,9 +578,6 @@ void launch_tc_prep(const float* theta, const PrepLayout& L, const float* scale_
     tc_prep_kernel<<<148, 256, 0, s>>>(theta, L, scale_dev, out);
 }
 void launch_tc_vscale(const float* v, int d, float* out2, cudaStream_t s) { tc_vscale_kernel<<<1, 1024, 0, s>>>(v, d, out2); }
-void launch_tc_scale_fix(const double* in2, const float* vscale2, double* out2, cudaStream_t s) {
-    tc_scale_fix_kernel<<<1, 1, 0, s>>>(in2, vscale2, out2);
-}
 
 cudaError_t launch_fvp_tc(const PrepLayout& L, const unsigned char* P, const unsigned char* T, const float* in_shift,
                           const float* in_scale, const float* out_scale, const float* obs, const int* idx, long long n,

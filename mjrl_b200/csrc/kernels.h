@@ -72,12 +72,13 @@ void launch_clamp_tail(float* theta, int d, int A, float lo, cudaStream_t s);
 // out[i] = scale * sum_c partial[c][i]  (+ log_std block of the FVP: c(sigma) * v for i >= tLS)
 void launch_reduce_partials(const float* partial, int grid, long long stride, int d, const double* scale_dev,
                             float* out, const float* theta, const float* v, int tLS, int fvp_ls_block,
-                            cudaStream_t s);
+                            const float* vscale2, cudaStream_t s);
 void launch_reduce_eval(const double* partial, int grid, double* out2, cudaStream_t s);
 // CG state lives on device: st = {rdotr, done_flag(as double), iters_run, g.x}
-void launch_cg_init(const float* b, float* x, float* r, float* p, int d, double* st, cudaStream_t s);
+// vscale2 (nullable): also emit the power-of-two scale {s, 1/s} of the new search direction p (tensor-core FVP)
+void launch_cg_init(const float* b, float* x, float* r, float* p, int d, double* st, float* vscale2, cudaStream_t s);
 void launch_cg_update(const float* Fp, float damping, float tol, float* x, float* r, float* p, int d,
-                      double* st, cudaStream_t s);
+                      double* st, float* vscale2, cudaStream_t s);
 void launch_dot(const float* a, const float* b, int d, double* out, cudaStream_t s);
 void launch_axpy_clamp(const float* theta, const float* x, const double* alpha_dev, double alpha_scale,
                        int d, int A, float lo, float* out, cudaStream_t s);
@@ -88,7 +89,6 @@ size_t fvp_tc_prep_bytes();
 bool fvp_tc_supported(const PrepLayout& L);
 void launch_tc_prep(const float* theta, const PrepLayout& L, const float* scale_dev, unsigned char* out, cudaStream_t s);
 void launch_tc_vscale(const float* v, int d, float* out2, cudaStream_t s);
-void launch_tc_scale_fix(const double* in2, const float* vscale2, double* out2, cudaStream_t s);
 cudaError_t launch_fvp_tc(const PrepLayout& L, const unsigned char* P, const unsigned char* T, const float* in_shift,
                           const float* in_scale, const float* out_scale, const float* obs, const int* idx, long long n,
                           float* gpartial, long long gstride, int grid, cudaStream_t s);

@@ -97,6 +97,10 @@ __global__ void __launch_bounds__(512, 1) linear_tc_kernel(const LinTcArgs a) {
     if (warp == 0) tmem_alloc(&s_tmem, TL_COLS);
     if (tid == 0) { for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1); }
     for (int i = tid; i < DY_BYTES / 16; i += 512) reinterpret_cast<uint4*>(smem + SL_DY)[i] = make_uint4(0, 0, 0, 0);
+    {   // this CTA's gradient partial starts at zero (no memset node in front of the kernel); gstride is a multiple of 32
+        float4* gz = reinterpret_cast<float4*>(a.gpartial + (size_t)blockIdx.x * a.gstride);
+        for (int i = tid; i < (int)(a.gstride / 4); i += 512) gz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     for (int k = tid; k < LKP; k += 512) {
         sf[SLF_SHIFT + k] = k < K0 ? a.in_shift[k] : 0.0f;
         sf[SLF_RINV + k] = k < K0 ? 1.0f / (a.in_scale[k] + 1e-8f) : 0.0f;

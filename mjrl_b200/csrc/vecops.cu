@@ -78,9 +78,11 @@ void launch_clamp_tail(float* theta, int d, int A, float lo, cudaStream_t s) {
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int grid, long long stride, int d,
                                        const double* __restrict__ scale_dev, float* __restrict__ out,
                                        const float* __restrict__ theta, const float* __restrict__ v, int tLS,
-                                       int fvp_ls_block) {
+                                       int fvp_ls_block, const float* __restrict__ vscale) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d) return;
+    // tensor-core FVP: the tangent was multiplied by the power of two vscale[0]; vscale[1] = 1/vscale[0] undoes it exactly
+    const double sc0 = vscale ? scale_dev[0] * (double)vscale[1] : scale_dev[0];
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     int c = 0;
     for (; c + 3 < grid; c += 4) {
@@ -90,7 +92,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int gr
         s3 += partial[(size_t)(c + 3) * stride + i];
     }
     for (; c < grid; ++c) s0 += partial[(size_t)c * stride + i];
-    float r = (float)((double)((s0 + s1) + (s2 + s3)) * (*scale_dev));
+    float r = (float)((double)((s0 + s1) + (s2 + s3)) * sc0);
     if (fvp_ls_block && i >= tLS) {
         const float u = expf(2.0f * theta[i]);
         const float den = 2.0f * u + 1e-8f;
@@ -102,9 +104,9 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int gr
 }
 void launch_reduce_partials(const float* partial, int grid, long long stride, int d, const double* scale_dev,
                             float* out, const float* theta, const float* v, int tLS, int fvp_ls_block,
-                            cudaStream_t s) {
+                            const float* vscale, cudaStream_t s) {
     reduce_partials_kernel<<<(d + 127) / 128, 128, 0, s>>>(partial, grid, stride, d, scale_dev, out, theta, v, tLS,
-                                                         fvp_ls_block);
+                                                         fvp_ls_block, vscale);
 }
 
 __global__ void reduce_eval_kernel(const double* __restrict__ partial, int grid, double* __restrict__ out2) {
@@ -121,26 +123,50 @@ void launch_reduce_eval(const double* partial, int grid, double* out2, cudaStrea
 
 // ---- conjugate gradient, state on device: st[0]=r.r  st[1]=done  st[2]=FVPs consumed  st[3]=scratch ----
 constexpr int kCgThreads = 1024;
-__global__ void cg_init_kernel(const float* __restrict__ b, float* x, float* r, float* p, int d, double* st) {
+// Block-wide max of |v| -> the power of two that brings it into [1, 2): out[0] = scale, out[1] = 1/scale.  The
+// tensor-core FVP multiplies its tangent by out[0] (two-term fp16 operands want O(1) magnitudes) and the reduction
+// multiplies by out[1]; both are exact.  Fused here so that the CG iteration has no separate scale kernel.
+__device__ __forceinline__ void block_pow2_scale(float mx, float* out, float* red) {
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+        int e = 0;
+        float s = 1.0f;
+        if (mx > 0.0f && isfinite(mx)) { frexpf(mx, &e); s = ldexpf(1.0f, 1 - e); }
+        out[0] = s;
+        out[1] = 1.0f / s;
+    }
+}
+
+__global__ void cg_init_kernel(const float* __restrict__ b, float* x, float* r, float* p, int d, double* st,
+                               float* vscale) {
     __shared__ double red[32];
+    __shared__ float redf[32];
     double s = 0.0;
+    float mx = 0.0f;
     for (int i = threadIdx.x; i < d; i += blockDim.x) {
         const float v = b[i];
         x[i] = 0.0f; r[i] = v; p[i] = v;
         s += (double)v * (double)v;
+        mx = fmaxf(mx, fabsf(v));
     }
     s = block_sum(s, red);
     if (threadIdx.x == 0) { st[0] = (double)(float)s; st[1] = 0.0; st[2] = 0.0; }
+    if (vscale) block_pow2_scale(mx, vscale, redf);
 }
-void launch_cg_init(const float* b, float* x, float* r, float* p, int d, double* st, cudaStream_t s) {
-    cg_init_kernel<<<1, kCgThreads, 0, s>>>(b, x, r, p, d, st);
+void launch_cg_init(const float* b, float* x, float* r, float* p, int d, double* st, float* vscale, cudaStream_t s) {
+    cg_init_kernel<<<1, kCgThreads, 0, s>>>(b, x, r, p, d, st, vscale);
 }
 
 // One iteration of cg_solve.py:10-20 given Fp (already all-reduced, undamped): z = Fp + damping*p, ...
 // Scalars are rounded to fp32 where the reference's numpy arithmetic is fp32 (A2).
 __global__ void cg_update_kernel(const float* __restrict__ Fp, float damping, float tol, float* x, float* r,
-                                 float* p, int d, double* st) {
+                                 float* p, int d, double* st, float* vscale) {
     __shared__ double red[32];
+    __shared__ float redf[32];
     __shared__ float s_alpha, s_mu;
     if (st[1] != 0.0) return;                           // converged earlier: x frozen (break at :19-20)
     double pz = 0.0;
@@ -164,16 +190,22 @@ __global__ void cg_update_kernel(const float* __restrict__ Fp, float damping, fl
     if (threadIdx.x == 0) s_mu = (float)rr / (float)st[0];
     __syncthreads();
     const float mu = s_mu;
-    for (int i = threadIdx.x; i < d; i += blockDim.x) p[i] = fmaf(mu, p[i], r[i]);
+    float mx = 0.0f;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+        const float pn = fmaf(mu, p[i], r[i]);
+        p[i] = pn;
+        mx = fmaxf(mx, fabsf(pn));
+    }
     if (threadIdx.x == 0) {
         st[0] = (double)(float)rr;
         st[2] += 1.0;
         if ((float)rr < tol) st[1] = 1.0;
     }
+    if (vscale) block_pow2_scale(mx, vscale, redf);     // scale of the NEXT Fisher product's tangent
 }
 void launch_cg_update(const float* Fp, float damping, float tol, float* x, float* r, float* p, int d, double* st,
-                      cudaStream_t s) {
-    cg_update_kernel<<<1, kCgThreads, 0, s>>>(Fp, damping, tol, x, r, p, d, st);
+                      float* vscale, cudaStream_t s) {
+    cg_update_kernel<<<1, kCgThreads, 0, s>>>(Fp, damping, tol, x, r, p, d, st, vscale);
 }
 
 __global__ void dot_kernel(const float* __restrict__ a, const float* __restrict__ b, int d, double* out) {

