@@ -503,6 +503,8 @@ def run_gpu(args, cfg, rank, world, local_rank):
     by = 4.0 * n_local * cfg["obs"]
     linear = len(cfg["hidden"]) == 0
     t = fvp_ms_kernel * 1e-3
+    if not t > 0:
+        raise SystemExit("no FVP kernel timing was recorded inside the timed steps (fvp_kernel_ms = %r)" % fvp_ms_kernel)
     prof = {}
     pj = os.path.join(ROOT, "profiles", "fvp_ncu_%s.json" % args.config)
     if os.path.exists(pj):

@@ -113,7 +113,7 @@ struct mjb_engine {
     float* vf_feat = nullptr; float* vf_ret32 = nullptr; long long vf_feat_cap = 0;   // fp32 features / targets of the fit
     int vf_tc_on = 1;         // fit kernel: 1 = single-SM tensor-core kernel where the shape allows, 0 = single-CTA FMA kernel
     int vf_sms = 1;           // SMs the fit kernel in flight occupies
-    float2* vf_consts = nullptr; int vf_consts_cap = 0;   // per-step Adam constants of the fit kernels
+    float4* vf_consts = nullptr; int vf_consts_cap = 0;   // per-step Adam constants of the fit kernels
     int* perm_dev = nullptr; long long perm_cap = 0;
     // global (all-rank) copies used by the replicated fit when world_size > 1
     float* fit_obs = nullptr; int* fit_tstep = nullptr; double* fit_ret = nullptr; long long fit_cap = 0;
@@ -283,6 +283,9 @@ int ensure_old_cache(mjb_engine* e, long long rows) {
 int fvp_device(mjb_engine* e, const float* v, const int* idx, long long n_idx, float* out, bool have_vscale = false,
                cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr) {
     const long long n = idx ? n_idx : e->n_roll;
+    // events handed in belong to a graph being captured: they become EXTERNAL event-record nodes, which is what makes
+    // cudaEventElapsedTime on them legal after a replay
+    const unsigned evflag = ev0 ? cudaEventRecordExternal : cudaEventRecordDefault;
     if (!ev0) {
         const int slot = (int)(e->fvp_count % mjb_engine::kFvpRing);
         ev0 = e->fvp_ev[slot][0]; ev1 = e->fvp_ev[slot][1];
@@ -291,20 +294,20 @@ int fvp_device(mjb_engine* e, const float* v, const int* idx, long long n_idx, f
     if (e->tc_ok && e->tc_on) {
         // tensor-core path: scale v to O(1) (exact power of two), split to fp16 hi/lo, tcgen05 tile kernel
         if (!have_vscale) { launch_tc_vscale(v, e->d, e->tc_vscale, e->stream); e->launches += 1; }
-        if (e->linear) launch_lin_tc_prep(v, e->cfg.obs_dim, e->A, e->tc_vscale, e->tc_prep_tan, e->stream);
+        if (e->linear) launch_lin_tc_prep(v, e->cfg.obs_dim, e->A, idx != nullptr, e->tc_vscale, e->tc_prep_tan, e->stream);
         else launch_tc_prep(v, e->PL, e->tc_vscale, e->tc_prep_tan, e->stream);
         const int sms = e->num_sms - (e->fit_in_flight ? e->vf_sms : 0);
         const int tile_rows = e->linear ? 64 : 128;
         const long long tiles = (n + tile_rows - 1) / tile_rows;
         const int grid = (int)std::max<long long>(1, std::min<long long>(tiles, sms));
-        CK(e, cudaEventRecord(ev0, e->stream));                 // (the kernels zero their own gradient partials)
+        CK(e, cudaEventRecordWithFlags(ev0, e->stream, evflag));   // (the kernels zero their own gradient partials)
         cudaError_t ce = e->linear
             ? launch_linear_tc(e->tc_prep_tan, e->pnew.theta, e->pnew.in_shift, e->pnew.in_scale, e->pnew.out_scale,
                                e->pnew.in_ident, e->obs, e->cfg.obs_dim, e->A, idx, n, e->gpartial, e->gstride, e->LL.tW, e->LL.tb, e->LL.tLS, grid, e->stream)
             : launch_fvp_tc(e->PL, e->tc_prep_new, e->tc_prep_tan, e->pnew.in_shift, e->pnew.in_scale,
                             e->pnew.out_scale, e->obs, idx, n, e->gpartial, e->gstride, grid, e->stream);
         if (ce != cudaSuccess) FAIL(e, std::string("fvp_tc launch: ") + cudaGetErrorString(ce));
-        CK(e, cudaEventRecord(ev1, e->stream));
+        CK(e, cudaEventRecordWithFlags(ev1, e->stream, evflag));
         launch_reduce_partials(e->gpartial, grid, e->gstride, e->d, e->dsc + (idx ? DS_SCALE_SUB : DS_SCALE), out,
                                e->pnew.theta, v, e->tLS, 1, e->tc_vscale, e->stream);
         e->launches += 3;
@@ -315,10 +318,10 @@ int fvp_device(mjb_engine* e, const float* v, const int* idx, long long n_idx, f
     else launch_prep_mlp(v, e->PL, e->prep_tan, e->stream);
     e->launches += 1;
     // the memset of the gradient partials belongs to the FVP; the event pair brackets memset + tile kernel
-    CK(e, cudaEventRecord(ev0, e->stream));
+    CK(e, cudaEventRecordWithFlags(ev0, e->stream, evflag));
     int grid = run_policy(e, MODE_FVP, e->pnew, e->prep_tan, n, idx, nullptr, 0);
     if (grid < 0) return -1;
-    CK(e, cudaEventRecord(ev1, e->stream));
+    CK(e, cudaEventRecordWithFlags(ev1, e->stream, evflag));
     launch_reduce_partials(e->gpartial, grid, e->gstride, e->d, e->dsc + (idx ? DS_SCALE_SUB : DS_SCALE), out,
                            e->pnew.theta, v, e->tLS, 1, nullptr, e->stream);
     e->launches += 1;
@@ -1186,7 +1189,7 @@ static int vf_fit_launch(mjb_engine* e, const int32_t* perms, int epochs, int ba
         if (steps > e->vf_consts_cap) {
             if (e->vf_consts) cudaFree(e->vf_consts);
             e->vf_consts_cap = steps + 1024;
-            CK(e, cudaMalloc(&e->vf_consts, sizeof(float2) * (size_t)e->vf_consts_cap));
+            CK(e, cudaMalloc(&e->vf_consts, sizeof(float4) * (size_t)e->vf_consts_cap));
         }
     }
     CK(e, cudaStreamSynchronize(e->stream));                 // host permutation buffer consumed; inputs of the fit complete
@@ -1256,12 +1259,12 @@ int mjb_dev_vf_profile(mjb_engine* e, long long* out16, int enable) {
 }
 
 // Developer aid: per-phase cycle counters of the tensor-core linear-policy FVP kernel (summed over CTAs).
-int mjb_dev_lin_profile(mjb_engine* e, long long* out8, int enable) {
+int mjb_dev_lin_profile(mjb_engine* e, long long* out8 /* 16 values */, int enable) {
     static unsigned long long* dev = nullptr;
-    if (!dev) { CK(e, cudaMalloc(&dev, 8 * sizeof(long long))); }
-    if (enable) { CK(e, cudaMemset(dev, 0, 8 * sizeof(long long))); lin_tc_set_prof(dev); return 0; }
+    if (!dev) { CK(e, cudaMalloc(&dev, 16 * sizeof(long long))); }
+    if (enable) { CK(e, cudaMemset(dev, 0, 16 * sizeof(long long))); lin_tc_set_prof(dev); return 0; }
     CK(e, cudaStreamSynchronize(e->stream));
-    CK(e, cudaMemcpy(out8, dev, 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    CK(e, cudaMemcpy(out8, dev, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
     lin_tc_set_prof(nullptr);
     return 0;
 }

@@ -97,7 +97,8 @@ cudaError_t launch_fvp_tc(const PrepLayout& L, const unsigned char* P, const uns
 size_t lin_tc_prep_bytes();
 bool lin_tc_supported(int K0, int A);
 void lin_tc_set_prof(unsigned long long* p);
-void launch_lin_tc_prep(const float* v, int K0, int A, const float* scale_dev, unsigned char* out, cudaStream_t s);
+// has_idx: the product will gather a subsample (selects the tangent layout of the kernel that will run)
+void launch_lin_tc_prep(const float* v, int K0, int A, bool has_idx, const float* scale_dev, unsigned char* out, cudaStream_t s);
 cudaError_t launch_linear_tc(const unsigned char* T, const float* theta, const float* in_shift, const float* in_scale,
                              const float* out_scale, bool identity_in, const float* obs, int K0, int A, const int* idx,
                              long long n, float* gpartial, long long gstride, int tW, int tb, int tLS, int grid, cudaStream_t s);
@@ -117,11 +118,11 @@ struct VfFitArgs {
 cudaError_t launch_vf_fit(const VfFitArgs& a, cudaStream_t s);
 // vf_fit_tc.cu : fp32 feature matrix + targets of the whole batch (built once per fit)
 cudaError_t vf_build_features(const VfFitArgs& a, float* feat, float* ret32, cudaStream_t s);
-// consts: caller-owned scratch of >= a.steps float2 (per-step Adam bias-correction constants, filled by the launcher)
+// consts: caller-owned scratch of >= a.steps float4 (per-step Adam bias-correction constants, filled by the launcher)
 // vf_fit_tc.cu : same chain on one SM with tcgen05 (units on the M axis, Adam moments of W2 in TMEM)
 bool vf_tc_supported(int K, int H1, int H2, int batch);
 void vf_tc_set_prof(long long* dev16);
-cudaError_t launch_vf_fit_tc(const VfFitArgs& a, const float* feat, const float* ret32, float2* consts, cudaStream_t s);
+cudaError_t launch_vf_fit_tc(const VfFitArgs& a, const float* feat, const float* ret32, float4* consts, cudaStream_t s);
 // err = sum((ret - pred)^2) / (sum(ret^2) + 1e-8) pieces: out = {sum err^2, sum ret^2} (fp32 casts like the reference)
 void launch_vf_error(const double* ret, const float* pred, long long n, double* scratch, double* out2, cudaStream_t s);
 

@@ -39,6 +39,12 @@ __global__ void __launch_bounds__(kThreads, 2) linear_kernel(const LinArgs a) {
     const int mq = tid % 32, ag = tid / 32;              // forward: 4 samples x AG outputs (a = ag + 8 i)
     const int nchunk = L.K0P / kChunk;
     if (tid < 32) s_gs[tid] = 0.0f;
+    // log_std gradient: per-thread running sums, reduced once at the end in a fixed order (no floating-point atomics)
+    float gs_acc[32];
+    if (MODE == MODE_VPG) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) gs_acc[j] = 0.0f;
+    }
     double sum0 = 0.0, sum1 = 0.0;
     float sum_ls = 0.0f;
     for (int j = 0; j < A; ++j) sum_ls += P[L.oLS + j];
@@ -121,7 +127,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_kernel(const LinArgs a) {
 #pragma unroll 1
                         for (int j = 0; j < A; ++j) {
                             ydT[j * LLDM + tid] *= coef;
-                            atomicAdd(&s_gs[j], coef * (zz[j] * zz[j] - 1.0f));
+                            gs_acc[j] += coef * (zz[j] * zz[j] - 1.0f);
                         }
                     }
                 } else if (MODE == MODE_VPG) {
@@ -160,8 +166,18 @@ __global__ void __launch_bounds__(kThreads, 2) linear_kernel(const LinArgs a) {
         if (tid == 0) { a.eval_partial[2 * blockIdx.x] = t0; a.eval_partial[2 * blockIdx.x + 1] = t1; }
     }
     if (MODE == MODE_VPG) {
+        __syncthreads();                                   // xs is free now: [warps][32] scratch
+#pragma unroll 1
+        for (int j = 0; j < A; ++j) {
+            const float t = warp_sum(gs_acc[j]);
+            if ((tid & 31) == 0) xs[(tid >> 5) * 32 + j] = t;
+        }
         __syncthreads();
-        if (tid < A) gp[L.tLS + tid] += s_gs[tid];
+        if (tid < A) {
+            float t = 0.0f;
+            for (int w = 0; w < kThreads / 32; ++w) t += xs[w * 32 + tid];
+            gp[L.tLS + tid] += t;
+        }
     }
 }
 

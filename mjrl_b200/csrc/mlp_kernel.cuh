@@ -203,6 +203,14 @@ __global__ void __launch_bounds__(kThreads, (H <= 64 ? 2 : 1)) mlp_kernel(const 
 
     for (int i = tid; i < L.YR * LDM; i += kThreads) ydT[i] = 0.0f;
     if (tid < 32) s_gs[tid] = 0.0f;
+    // log_std gradient: per-thread running sums over this CTA's tiles (thread = row of the tile), reduced once at the end
+    // in a fixed order (warp xor-tree, then warps 0..7) -- no floating-point atomics, so the flat gradient is
+    // bit-reproducible run to run.
+    float gs_acc[32];
+    if (MODE == MODE_VPG) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) gs_acc[j] = 0.0f;
+    }
     double sum0 = 0.0, sum1 = 0.0;
     float sum_ls = 0.0f;
     if (MODE == MODE_EVAL || MODE == MODE_VPG)
@@ -381,7 +389,7 @@ __global__ void __launch_bounds__(kThreads, (H <= 64 ? 2 : 1)) mlp_kernel(const 
 #pragma unroll 1
                         for (int j = 0; j < A; ++j) {
                             ydT[j * LDM + tid] *= coef;
-                            atomicAdd(&s_gs[j], coef * (zz[j] * zz[j] - 1.0f));
+                            gs_acc[j] += coef * (zz[j] * zz[j] - 1.0f);
                         }
                     }
                 } else if (MODE == MODE_VPG) {
@@ -518,8 +526,18 @@ __global__ void __launch_bounds__(kThreads, (H <= 64 ? 2 : 1)) mlp_kernel(const 
         if (tid == 0) { a.eval_partial[2 * blockIdx.x] = t0; a.eval_partial[2 * blockIdx.x + 1] = t1; }
     }
     if (MODE == MODE_VPG) {
+        __syncthreads();                                   // ydT is free now: [warps][32] scratch
+#pragma unroll 1
+        for (int j = 0; j < A; ++j) {
+            const float t = warp_sum(gs_acc[j]);
+            if ((tid & 31) == 0) ydT[(tid >> 5) * 32 + j] = t;
+        }
         __syncthreads();
-        if (tid < A) gp[L.tLS + tid] += s_gs[tid];
+        if (tid < A) {
+            float t = 0.0f;
+            for (int w = 0; w < kThreads / 32; ++w) t += ydT[w * 32 + tid];
+            gp[L.tLS + tid] += t;
+        }
     }
 }
 

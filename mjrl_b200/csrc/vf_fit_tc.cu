@@ -53,9 +53,10 @@ constexpr int F_VEC = F_W1V + KP * H;                                          /
 constexpr int F_B3 = F_VEC + 9 * H;                                            // b3 w,m,v (+pad)
 constexpr int F_YP = F_B3 + 4;                                                 // ypart[4][64]
 constexpr int F_GW3 = F_YP + 4 * NB, F_GB2 = F_GW3 + 4 * H, F_GB1 = F_GB2 + 4 * H, F_GB3 = F_GB1 + 4 * H;
-constexpr int F_T = F_GB3 + 4;                                                 // targets t[64]
-constexpr int F_END = F_T + NB;
-constexpr int S_BAR = S_F32 + F_END * 4;
+constexpr int F_T = F_GB3 + 4;                                                 // targets t[2][64] (double-buffered with X)
+constexpr int F_END = F_T + 2 * NB;
+constexpr int S_X2 = S_F32 + F_END * 4;                                        // second minibatch buffer [X hi | X lo]
+constexpr int S_BAR = S_X2 + 2 * X_BYTES;
 constexpr int S_TOTAL = S_BAR + 32;
 
 // TMEM columns.  D holds [X*hi | X*lo] halves of the N-concatenated products; gW1 reuses its columns (D is dead by then)
@@ -66,22 +67,39 @@ struct TcFitArgs {
     const float* feat; const float* ret32; const int* perm;
     float reg, beta1, beta2, eps;
     float* w; float* m; float* v;
-    const float2* consts;                    // per-step {1/sqrt(1-b2^t), -lr/(1-b1^t)}
+    const float4* consts;                    // per-step {1/sqrt(1-b2^t), -lr/(1-b1^t), sqrt(1-b2^t), -eps*sqrt(1-b2^t)}
     long long* prof;
 };
 
-struct AdamP { float one_m_b1, b2, one_m_b2, rbc2_sqrt, eps, neg_step, reg; };
+struct AdamP { float one_m_b1, b2, one_m_b2, rbc2_sqrt, eps, neg_step, reg, cinv, neg_ec; };
 
-// torch.optim.Adam update.  One SM updates all 20 k parameters every step, so the square root and the division use
-// the MUFU approximations (<= 2 ulp each, the same order as the two-term fp16 rounding of the GEMM operands).
+// torch.optim.Adam update: w -= step * m / (sqrt(v) / sqrt(1 - b2^t) + eps).  One SM updates all 20 k parameters every
+// step and the MUFU unit (16 results / clock / SM) is what bounds that, so the quotient costs ONE MUFU op, not two:
+//   r = rsqrt(v),  1 / (sqrt(v) c + eps) = (r / c) / (1 + q),  q = eps r / c,  1 / (1 + q) = 1 - q + q^2 - q^3 + O(q^4)
+// with the series on the FMA pipe.  q is ~1e-4 .. 1e-3 for every parameter that sees a gradient; lanes with q > 0.01
+// (error 1e-8 at the threshold), v == 0 or a non-finite r take the two-MUFU form sqrt + rcp.  Either way the error is
+// <= 2 ulp, the same order as the two-term fp16 rounding of the GEMM operands.
+__device__ __forceinline__ float adam_inv_slow(float v, const AdamP& c) {
+    float sq, rc;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(v));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fmaf(sq, c.rbc2_sqrt, c.eps)));
+    return rc;
+}
 __device__ __forceinline__ float adam_apply(float g, float w, float& m, float& v, const AdamP& c) {
     g = fmaf(c.reg, w, g);
     m = fmaf(c.one_m_b1, g - m, m);
     v = fmaf(c.one_m_b2 * g, g, v * c.b2);
-    float sq, rc;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(v));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fmaf(sq, c.rbc2_sqrt, c.eps)));
-    return fmaf(c.neg_step, m * rc, w);
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    const float nq = r * c.neg_ec;                                   // -q
+    float inv;
+    if (nq >= -0.01f) {
+        const float p = fmaf(nq, fmaf(nq, 1.0f + nq, 1.0f), 1.0f);   // 1 - q + q^2 - q^3
+        inv = (r * c.cinv) * p;
+    } else {
+        inv = adam_inv_slow(v, c);
+    }
+    return fmaf(c.neg_step, m * inv, w);
 }
 
 // ---- packed fp32x2 arithmetic (sm_100 FFMA2 / FMUL2 / FADD2): two IEEE-rounded lanes per instruction, bit-identical to
@@ -93,11 +111,11 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm(
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
-struct AdamP2 { f32x2 one_m_b1, b2, one_m_b2, rbc2_sqrt, eps, neg_step, reg, gscale; };
+struct AdamP2 { f32x2 one_m_b1, b2, one_m_b2, neg_step, reg, gscale, cinv, neg_ec, one; };
 
 // two parameters at once; same operation sequence as adam_apply (so the results are bit-identical)
 __device__ __forceinline__ void adam_apply2(float g0, float g1, float& w0, float& w1, float& m0, float& m1, float& v0, float& v1,
-                                            const AdamP2& c) {
+                                            const AdamP2& c, const AdamP& cs) {
     const f32x2 w = pk2(w0, w1);
     f32x2 m = pk2(m0, m1), v = pk2(v0, v1);
     f32x2 g = mul2(pk2(g0, g1), c.gscale);
@@ -105,14 +123,21 @@ __device__ __forceinline__ void adam_apply2(float g0, float g1, float& w0, float
     m = fma2(c.one_m_b1, sub2(g, m), m);
     v = fma2(mul2(c.one_m_b2, g), g, mul2(v, c.b2));
     upk2(v, v0, v1);
-    float s0, s1, r0, r1;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s0) : "f"(v0));
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s1) : "f"(v1));
-    float d0, d1;
-    upk2(fma2(pk2(s0, s1), c.rbc2_sqrt, c.eps), d0, d1);
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
-    upk2(fma2(c.neg_step, mul2(m, pk2(r0, r1)), w), w0, w1);
+    float r0, r1;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(v0));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(v1));
+    const f32x2 r = pk2(r0, r1);
+    const f32x2 nq = mul2(r, c.neg_ec);                              // -q (both lanes)
+    float nq0, nq1;
+    upk2(nq, nq0, nq1);
+    f32x2 inv;
+    if (nq0 >= -0.01f && nq1 >= -0.01f) {                            // (NaN / inf fail the comparison -> slow path)
+        const f32x2 p = fma2(nq, fma2(nq, fma2(nq, c.one, c.one), c.one), c.one);     // 1 - q + q^2 - q^3
+        inv = mul2(mul2(r, c.cinv), p);
+    } else {
+        inv = pk2(adam_inv_slow(v0, cs), adam_inv_slow(v1, cs));
+    }
+    upk2(fma2(c.neg_step, mul2(m, inv), w), w0, w1);
     upk2(m, m0, m1);
 }
 
@@ -129,30 +154,38 @@ __device__ __forceinline__ void split8_store(const float (&x)[8], unsigned char*
     *reinterpret_cast<uint4*>(lo) = *reinterpret_cast<const uint4*>(l);
 }
 
-// D (+)= A B^T over `ksteps` 16-element reduction steps with two-term operands (hi*hi + lo*hi + hi*lo)
+// D (+)= A B^T over KS 16-element reduction steps with two-term operands (hi*hi + lo*hi + hi*lo).  Descriptors are built
+// once and advanced by one add per step (tc_common.cuh: desc_adv); the loop is fully unrolled.
+template <int KS>
 __device__ __forceinline__ void gemm3(uint32_t d, uint32_t ah, uint32_t al, uint32_t a_step, uint32_t a_lbo, uint32_t a_sbo,
-                                      uint32_t bh, uint32_t bl, uint32_t b_step, uint32_t b_lbo, uint32_t b_sbo, int ksteps,
-                                      uint32_t idesc) {
-    for (int j = 0; j < ksteps; ++j) {
-        const uint64_t dah = make_desc(ah + j * a_step, a_lbo, a_sbo), dal = make_desc(al + j * a_step, a_lbo, a_sbo);
-        const uint64_t dbh = make_desc(bh + j * b_step, b_lbo, b_sbo), dbl = make_desc(bl + j * b_step, b_lbo, b_sbo);
+                                      uint32_t bh, uint32_t bl, uint32_t b_step, uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc) {
+    uint64_t dah = make_desc(ah, a_lbo, a_sbo), dal = make_desc(al, a_lbo, a_sbo);
+    uint64_t dbh = make_desc(bh, b_lbo, b_sbo), dbl = make_desc(bl, b_lbo, b_sbo);
+#pragma unroll
+    for (int j = 0; j < KS; ++j) {
         mma_f16(d, dah, dbh, idesc, j > 0);
         mma_f16(d, dal, dbh, idesc, true);
         mma_f16(d, dah, dbl, idesc, true);
+        dah = desc_adv(dah, a_step); dal = desc_adv(dal, a_step);
+        dbh = desc_adv(dbh, b_step); dbl = desc_adv(dbl, b_step);
     }
 }
 
 // Same product with the B terms N-concatenated: the buffer pair [B hi | B lo] is contiguous along N, so
 //   D[:, 0:n] (+)= A_hi B_hi + A_lo B_hi   and   D[:, n:2n] (+)= A_hi B_lo     -- two MMAs per step instead of three;
 // the epilogue adds the two column halves.
+template <int KS>
 __device__ __forceinline__ void gemm2c(uint32_t d, uint32_t ah, uint32_t al, uint32_t a_step, uint32_t a_lbo, uint32_t a_sbo,
-                                       uint32_t bh, uint32_t b_step, uint32_t b_lbo, uint32_t b_sbo, int ksteps,
+                                       uint32_t bh, uint32_t b_step, uint32_t b_lbo, uint32_t b_sbo,
                                        uint32_t idesc_2n, uint32_t idesc_n) {
-    for (int j = 0; j < ksteps; ++j) {
-        const uint64_t dah = make_desc(ah + j * a_step, a_lbo, a_sbo), dal = make_desc(al + j * a_step, a_lbo, a_sbo);
-        const uint64_t dbh = make_desc(bh + j * b_step, b_lbo, b_sbo);
+    uint64_t dah = make_desc(ah, a_lbo, a_sbo), dal = make_desc(al, a_lbo, a_sbo);
+    uint64_t dbh = make_desc(bh, b_lbo, b_sbo);
+#pragma unroll
+    for (int j = 0; j < KS; ++j) {
         mma_f16(d, dah, dbh, idesc_2n, j > 0);
         mma_f16(d, dal, dbh, idesc_n, true);
+        dah = desc_adv(dah, a_step); dal = desc_adv(dal, a_step);
+        dbh = desc_adv(dbh, b_step);
     }
 }
 
@@ -236,7 +269,10 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
         for (int j = 0; j < 4; ++j) xr[j] = (gk + j < K) ? p[j] : 0.0f;
         if (gk == 0) tt = a.ret32[idx];
     };
-    auto stage_x = [&]() {
+    // The minibatch operand is double-buffered (step parity): the rows of step s+1 are staged while the gW2 GEMM of step
+    // s runs and nobody else has work, instead of on the critical path after the last GEMM of the step.
+    auto stage_x = [&](int par) {
+        const int xo = par ? S_X2 : S_XH;
         const float s0 = SA * xr[0], s1 = SA * xr[1], s2 = SA * xr[2], s3 = SA * xr[3];
         const __half2 h01 = __floats2half2_rn(s0, s1), h23 = __floats2half2_rn(s2, s3);
         const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
@@ -244,13 +280,14 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
         uint2 hv, lv;
         hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
         lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
-        *reinterpret_cast<uint2*>(smem + S_XH + xoff) = hv;
-        *reinterpret_cast<uint2*>(smem + S_XL + xoff) = lv;
-        if (gk == 0) sf[F_T + gn] = tt;
+        *reinterpret_cast<uint2*>(smem + xo + xoff) = hv;
+        *reinterpret_cast<uint2*>(smem + xo + X_BYTES + xoff) = lv;
+        if (gk == 0) sf[F_T + par * NB + gn] = tt;
     };
     int i1 = 0, i2 = 0;
+    float4 cst_next = a.consts[0];                                   // Adam constants: prefetched one step ahead
     load_rows(a.perm[gn]);
-    stage_x();
+    stage_x(0);
     if (a.steps > 1) i1 = a.perm[NB + gn];
     if (a.steps > 2) i2 = a.perm[2 * NB + gn];
 
@@ -271,23 +308,27 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
     ap.one_m_b1 = 1.0f - a.beta1; ap.b2 = a.beta2; ap.one_m_b2 = 1.0f - a.beta2; ap.eps = a.eps; ap.reg = a.reg;
     AdamP2 ap2;
     ap2.one_m_b1 = pk2(ap.one_m_b1, ap.one_m_b1); ap2.b2 = pk2(ap.b2, ap.b2); ap2.one_m_b2 = pk2(ap.one_m_b2, ap.one_m_b2);
-    ap2.eps = pk2(ap.eps, ap.eps); ap2.reg = pk2(ap.reg, ap.reg); ap2.gscale = pk2(1.0f / (SG * SA), 1.0f / (SG * SA));
-    ap2.rbc2_sqrt = ap2.neg_step = 0;
+    ap2.reg = pk2(ap.reg, ap.reg); ap2.gscale = pk2(1.0f / (SG * SA), 1.0f / (SG * SA));
+    ap2.one = pk2(1.0f, 1.0f);
+    ap2.neg_step = ap2.cinv = ap2.neg_ec = 0;
+    ap.rbc2_sqrt = ap.neg_step = ap.cinv = ap.neg_ec = 0.0f;
 
     for (int s = 0; s < a.steps; ++s) {
         sync_ops();                                                  // X(s), weights(s) staged
         if (tid == 0) {                                              // layer 1: z1^T = W1 x^T
             tcgen05_fence_after();
-            gemm3(tmem + T_D, sbase + S_W1H, sbase + S_W1L, 2 * LB128, LB128, 128,
-                  sbase + S_XH, sbase + S_XL, 2 * LB64, LB64, 128, KP / 16, ID_L1);
+            const uint32_t xb = sbase + ((s & 1) ? S_X2 : S_XH);
+            gemm3<KP / 16>(tmem + T_D, sbase + S_W1H, sbase + S_W1L, 2 * LB128, LB128, 128,
+                           xb, xb + X_BYTES, 2 * LB64, LB64, 128, ID_L1);
             mma_commit(&bars[0]);
         }
         if (s + 1 < a.steps) load_rows(i1);                          // rows of step s+1: a whole step to land
         i1 = i2;
         if (s + 3 < a.steps) i2 = a.perm[(size_t)(s + 3) * NB + gn];
-        const float2 cst = a.consts[s];
-        ap.rbc2_sqrt = cst.x; ap.neg_step = cst.y;
-        ap2.rbc2_sqrt = pk2(cst.x, cst.x); ap2.neg_step = pk2(cst.y, cst.y);
+        const float4 cst = cst_next;
+        if (s + 1 < a.steps) cst_next = a.consts[s + 1];
+        ap.rbc2_sqrt = cst.x; ap.neg_step = cst.y; ap.cinv = cst.z; ap.neg_ec = cst.w;
+        ap2.neg_step = pk2(cst.y, cst.y); ap2.cinv = pk2(cst.z, cst.z); ap2.neg_ec = pk2(cst.w, cst.w);
         TC_PROF(0);
         wait0();
         TC_PROF(1);
@@ -315,8 +356,8 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
         TC_PROF(2);
         if (tid == 0) {                                              // layer 2: z2^T = W2 h1
             tcgen05_fence_after();
-            gemm2c(tmem + T_D, sbase + S_W2H, sbase + S_W2L, 2 * LB128, LB128, 128,
-                   sbase + S_HH, 2 * 128, 128, LB128, H / 16, ID_L2c, ID_L2);
+            gemm2c<H / 16>(tmem + T_D, sbase + S_W2H, sbase + S_W2L, 2 * LB128, LB128, 128,
+                           sbase + S_HH, 2 * 128, 128, LB128, ID_L2c, ID_L2);
             mma_commit(&bars[0]);
         }
         TC_PROF(3);
@@ -374,7 +415,7 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
                     const float4 p1 = *reinterpret_cast<const float4*>(sf + F_YP + NB + n0 + 4 * h4);
                     const float4 p2 = *reinterpret_cast<const float4*>(sf + F_YP + 2 * NB + n0 + 4 * h4);
                     const float4 p3 = *reinterpret_cast<const float4*>(sf + F_YP + 3 * NB + n0 + 4 * h4);
-                    const float4 t4 = *reinterpret_cast<const float4*>(sf + F_T + n0 + 4 * h4);
+                    const float4 t4 = *reinterpret_cast<const float4*>(sf + F_T + (s & 1) * NB + n0 + 4 * h4);
                     y[4 * h4 + 0] = (((p0.x + p1.x) + p2.x) + p3.x) + b3; y[4 * h4 + 1] = (((p0.y + p1.y) + p2.y) + p3.y) + b3;
                     y[4 * h4 + 2] = (((p0.z + p1.z) + p2.z) + p3.z) + b3; y[4 * h4 + 3] = (((p0.w + p1.w) + p2.w) + p3.w) + b3;
                     tg[4 * h4 + 0] = t4.x; tg[4 * h4 + 1] = t4.y; tg[4 * h4 + 2] = t4.z; tg[4 * h4 + 3] = t4.w;
@@ -399,14 +440,30 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
         TC_PROF(6);
         if (tid == 0) {                                              // gW2 = dz2 h1^T -> bar 1, then dh1^T = W2^T dz2 -> bar 0
             tcgen05_fence_after();
-            gemm3(tmem + T_G2, sbase + S_DH, sbase + S_DL, 2 * LB128, LB128, 128,
-                  sbase + S_HH, sbase + S_HL, 2 * LB128, LB128, 128, NB / 16, ID_G2);
+            gemm3<NB / 16>(tmem + T_G2, sbase + S_DH, sbase + S_DL, 2 * LB128, LB128, 128,
+                           sbase + S_HH, sbase + S_HL, 2 * LB128, LB128, 128, ID_G2);
             mma_commit(&bars[1]);
-            gemm2c(tmem + T_D, sbase + S_W2H, sbase + S_W2L, 2 * 128, 128, LB128,
-                   sbase + S_DH, 2 * 128, 128, LB128, H / 16, ID_DHc, ID_DH);
+            gemm2c<H / 16>(tmem + T_D, sbase + S_W2H, sbase + S_W2L, 2 * 128, 128, LB128,
+                           sbase + S_DH, 2 * 128, 128, LB128, ID_DHc, ID_DH);
             mma_commit(&bars[0]);
         }
         TC_PROF(7);
+        // ---- nothing depends on these until the next step: they run while the gW2 GEMM has the tensor pipe to itself ----
+        if (cq >= 2) {                                               // b2 (cq 2) and w3 (cq 3): gradients are complete after E2b
+            const int p = cq - 1;
+            const int gsrc = p == 1 ? F_GB2 : F_GW3;
+            const float g = ((sf[gsrc + u] + sf[gsrc + H + u]) + sf[gsrc + 2 * H + u]) + sf[gsrc + 3 * H + u];
+            float mj = sf[F_VEC + (3 * p + 1) * H + u], vj = sf[F_VEC + (3 * p + 2) * H + u];
+            sf[F_VEC + (3 * p + 0) * H + u] = adam_apply(g, sf[F_VEC + (3 * p + 0) * H + u], mj, vj, ap);
+            sf[F_VEC + (3 * p + 1) * H + u] = mj; sf[F_VEC + (3 * p + 2) * H + u] = vj;
+        }
+        if (tid == NT - 1) {
+            const float g = ((sf[F_GB3] + sf[F_GB3 + 1]) + sf[F_GB3 + 2]) + sf[F_GB3 + 3];
+            float mj = sf[F_B3 + 1], vj = sf[F_B3 + 2];
+            sf[F_B3] = adam_apply(g, sf[F_B3], mj, vj, ap);
+            sf[F_B3 + 1] = mj; sf[F_B3 + 2] = vj;
+        }
+        if (s + 1 < a.steps) stage_x((s + 1) & 1);                   // minibatch of step s+1 (rows loaded at the top of this step)
         wait1();                                                     // gW2 done: its Adam half runs under the dh1 GEMM
         auto adam_w2 = [&](int c16) {                                // W2[u][32cq + 16 c16 ..]: moments in TMEM
             uint32_t g[16], mm[16], vv[16];
@@ -418,7 +475,7 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
             for (int j = 0; j < 16; j += 2) {
                 float m0 = __uint_as_float(mm[j]), m1 = __uint_as_float(mm[j + 1]);
                 float v0 = __uint_as_float(vv[j]), v1 = __uint_as_float(vv[j + 1]);
-                adam_apply2(__uint_as_float(g[j]), __uint_as_float(g[j + 1]), w2[16 * c16 + j], w2[16 * c16 + j + 1], m0, m1, v0, v1, ap2);
+                adam_apply2(__uint_as_float(g[j]), __uint_as_float(g[j + 1]), w2[16 * c16 + j], w2[16 * c16 + j + 1], m0, m1, v0, v1, ap2, ap);
                 mm[j] = __float_as_uint(m0); mm[j + 1] = __float_as_uint(m1);
                 vv[j] = __float_as_uint(v0); vv[j + 1] = __float_as_uint(v1);
             }
@@ -463,26 +520,18 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
         TC_PROF(9);
         if (tid == 0) {                                              // gW1 = dz1 x -> bar 0, under the second Adam half of W2
             tcgen05_fence_after();
-            gemm2c(tmem + T_G1, sbase + S_DH, sbase + S_DL, 2 * LB128, LB128, 128,
-                   sbase + S_XH, 2 * 128, 128, LB64, NB / 16, ID_G1c, ID_G1);
+            gemm2c<NB / 16>(tmem + T_G1, sbase + S_DH, sbase + S_DL, 2 * LB128, LB128, 128,
+                            sbase + ((s & 1) ? S_X2 : S_XH), 2 * 128, 128, LB64, ID_G1c, ID_G1);
             mma_commit(&bars[0]);
         }
         store_w2(0);
         adam_w2(1);
         store_w2(1);
-        if (cq >= 1) {                                               // b1, b2, w3: one vector per column quarter 1..3 (the issuer's
-            const int p = cq - 1;                                    // quarter 0 stays light); fixed-order sums of the four partials
-            const int gsrc = p == 0 ? F_GB1 : (p == 1 ? F_GB2 : F_GW3);
-            const float g = ((sf[gsrc + u] + sf[gsrc + H + u]) + sf[gsrc + 2 * H + u]) + sf[gsrc + 3 * H + u];
-            float mj = sf[F_VEC + (3 * p + 1) * H + u], vj = sf[F_VEC + (3 * p + 2) * H + u];
-            sf[F_VEC + (3 * p + 0) * H + u] = adam_apply(g, sf[F_VEC + (3 * p + 0) * H + u], mj, vj, ap);
-            sf[F_VEC + (3 * p + 1) * H + u] = mj; sf[F_VEC + (3 * p + 2) * H + u] = vj;
-        }
-        if (tid == NT - 1) {
-            const float g = ((sf[F_GB3] + sf[F_GB3 + 1]) + sf[F_GB3 + 2]) + sf[F_GB3 + 3];
-            float mj = sf[F_B3 + 1], vj = sf[F_B3 + 2];
-            sf[F_B3] = adam_apply(g, sf[F_B3], mj, vj, ap);
-            sf[F_B3 + 1] = mj; sf[F_B3 + 2] = vj;
+        if (cq == 1) {                                               // b1 (its gradient is complete after E3); fixed-order sum
+            const float g = ((sf[F_GB1 + u] + sf[F_GB1 + H + u]) + sf[F_GB1 + 2 * H + u]) + sf[F_GB1 + 3 * H + u];
+            float mj = sf[F_VEC + 1 * H + u], vj = sf[F_VEC + 2 * H + u];
+            sf[F_VEC + u] = adam_apply(g, sf[F_VEC + u], mj, vj, ap);
+            sf[F_VEC + 1 * H + u] = mj; sf[F_VEC + 2 * H + u] = vj;
         }
         TC_PROF(10);
         wait0();                                                     // gW1 done (X and dz buffers free)
@@ -505,7 +554,6 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
             const uint32_t o = rowoff + (uint32_t)cq * LB128;
             split8_store(x, smem + S_W1H + o, smem + S_W1L + o);
         }
-        if (s + 1 < a.steps) stage_x();                              // minibatch of step s+1
         tmem_st_wait();
         TC_PROF(12);
     }
@@ -550,12 +598,12 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
     if (warp == 0) tmem_dealloc(tmem, T_COLS);
 }
 
-__global__ void tc_adam_consts_kernel(float2* out, int steps, long long step0, float lr, float beta1, float beta2) {
+__global__ void tc_adam_consts_kernel(float4* out, int steps, long long step0, float lr, float beta1, float beta2, float eps) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= steps) return;
     const double t = (double)(step0 + s + 1);
     const double bc1 = 1.0 - pow((double)beta1, t), bc2 = 1.0 - pow((double)beta2, t);
-    out[s] = make_float2((float)(1.0 / sqrt(bc2)), (float)(-((double)lr / bc1)));
+    out[s] = make_float4((float)(1.0 / sqrt(bc2)), (float)(-((double)lr / bc1)), (float)sqrt(bc2), (float)(-(double)eps * sqrt(bc2)));
 }
 
 long long* g_tc_prof = nullptr;
@@ -596,8 +644,8 @@ void vf_tc_set_prof(long long* dev16) { g_tc_prof = dev16; }
 
 bool vf_tc_supported(int K, int H1, int H2, int batch) { return batch == NB && H1 == H && H2 == H && K >= 1 && K <= KP; }
 
-cudaError_t launch_vf_fit_tc(const VfFitArgs& v, const float* feat, const float* ret32, float2* consts, cudaStream_t s) {
-    tc_adam_consts_kernel<<<(v.steps + 255) / 256, 256, 0, s>>>(consts, v.steps, v.step0, v.lr, v.beta1, v.beta2);
+cudaError_t launch_vf_fit_tc(const VfFitArgs& v, const float* feat, const float* ret32, float4* consts, cudaStream_t s) {
+    tc_adam_consts_kernel<<<(v.steps + 255) / 256, 256, 0, s>>>(consts, v.steps, v.step0, v.lr, v.beta1, v.beta2, v.eps);
     TcFitArgs a;
     a.K = v.K; a.steps = v.steps; a.feat = feat; a.ret32 = ret32; a.perm = v.perm;
     a.reg = v.reg; a.beta1 = v.beta1; a.beta2 = v.beta2; a.eps = v.eps;

@@ -174,7 +174,8 @@ def test_baseline_fit(case, tensor_cores, cuda_device):
     assert rel(w, g["fit2_w"]) < (6e-2 if long_chain else 2e-2)
     assert rel(vv, g["fit2_v"]) < (7e-3 if long_chain else 1e-3)
     eng.vf_predict()
-    np.testing.assert_allclose(eng.baseline(), g["fit2_predict"], rtol=0, atol=2e-4)
+    # (cheetah_24x500: the fp32 oracle's own predictions are 6.5e-3 away from the reference's after the second call)
+    np.testing.assert_allclose(eng.baseline(), g["fit2_predict"], rtol=0, atol=2e-2 if long_chain else 2e-4)
     eng.close()
 
 

@@ -31,10 +31,21 @@ for tc in (True, False):
 eng.set_tensor_cores(True)
 eng.lib.mjb_dev_lin_profile(eng.h, None, 1)
 eng.fvp(v, 1e-4)
-out = (C.c_longlong * 8)()
+out = (C.c_longlong * 16)()
 eng.lib.mjb_dev_lin_profile(eng.h, out, 0)
-tiles = out[6]
-tot = sum(out[:6])
-print("tiles %d, %d cycles per tile (thread 0 of each CTA)" % (tiles, tot // max(tiles, 1)))
-for i, n in enumerate(names):
-    print("   %-62s %7d cyc  %5.1f%%" % (n, out[i] // max(tiles, 1), 100.0 * out[i] / tot))
+if out[11] > 0:      # TMA-fed kernel: per-role counters
+    tiles = out[11]
+    roles = [("converter warp 0", ["wait GEMM2 (+flush)", "wait ring slot full", "convert + STS + release", "wait GEMM1", "dy epilogue"], range(0, 5)),
+             ("MMA issuer", ["wait staged", "issue GEMM1", "wait dy", "issue GEMM2"], range(5, 9)),
+             ("TMA producer", ["wait slot empty", "issue row copies"], range(9, 11))]
+    for role, names_, idxs in roles:
+        tot = sum(out[i] for i in idxs)
+        print("%s: %d cycles per tile" % (role, tot // tiles))
+        for n_, i in zip(names_, idxs):
+            print("   %-32s %7d cyc  %5.1f%%" % (n_, out[i] // tiles, 100.0 * out[i] / max(tot, 1)))
+else:
+    tiles = out[6]
+    tot = sum(out[:6])
+    print("tiles %d, %d cycles per tile (thread 0 of each CTA)" % (tiles, tot // max(tiles, 1)))
+    for i, n in enumerate(names):
+        print("   %-62s %7d cyc  %5.1f%%" % (n, out[i] // max(tiles, 1), 100.0 * out[i] / tot))
