@@ -142,6 +142,11 @@ int  mjb_policy_step(mjb_engine* e, int algo, double step_size_or_kl, double con
                      int cg_iters, float damping, double demo_lam, const int32_t* hvp_idx, int64_t n_idx,
                      mjb_step_stats* out);
 int  mjb_policy_last_vectors(mjb_engine* e, float* vpg_out, float* npg_out);   /* g and x of the last step */
+/* hvp_sample_frac < 1 under data parallelism (algos/npg_cg.py:65-69): the host draws GLOBAL sample indices,
+ * every rank keeps the ones inside its own row range, so the per-iteration lists differ in length between ranks and
+ * between iterations.  The index block of the NEXT mjb_policy_cg / mjb_policy_step call stays [iters][n_idx] (n_idx = the
+ * row stride); n_each[i] <= n_idx says how many entries of row i are valid.  One-shot: consumed by that call. */
+int  mjb_policy_set_hvp_lengths(mjb_engine* e, const int64_t* n_each, int iters);
 
 /* FVP arithmetic: 1 (default where supported: 128x128 MLP, obs < 32, act <= 8) = tcgen05 tensor cores with two-term
  * fp16 operand splitting (hi*hi + lo*hi + hi*lo, fp32 accumulation in TMEM); 0 = the fp32 FMA tile kernel.

@@ -77,6 +77,7 @@ _SIGNATURES = {
                                   C.c_int64, C.POINTER(StepStats)]),
     "mjb_policy_set_tensor_cores": (C.c_int, [_P, C.c_int]),
     "mjb_policy_last_vectors": (C.c_int, [_P, _P, _P]),
+    "mjb_policy_set_hvp_lengths": (C.c_int, [_P, _P, C.c_int]),
     "mjb_vf_dim": (C.c_int, [_P]),
     "mjb_vf_set_state": (C.c_int, [_P, _P, _P, _P, C.c_int64]),
     "mjb_vf_get_state": (C.c_int, [_P, _P, _P, _P, C.POINTER(C.c_int64)]),

@@ -48,21 +48,35 @@ class NPG(BatchREINFORCE):
         numpy RNG at the reference's program point (npg_cg.py:65-69)."""
         if self.hvp_subsample is None or self.hvp_subsample >= 0.99:
             return None
-        if self._engine is not None and self._engine.world_size > 1:
-            raise NotImplementedError("hvp_sample_frac < 1 with world_size > 1")
+        eng = self._engine
+        if eng is not None and eng.world_size > 1:
+            # Data parallel (SURVEY 8e): every rank draws the SAME global index sets (the ranks run the same program
+            # with the same numpy seed, as a single-process reference run would) and keeps the entries that fall into its
+            # own row range, rebased to local rows -- the union over the ranks is exactly the reference's subsample.
+            from mjrl_b200.parallel import local_subsample, sample_ranges
+            n_glob = eng.n_global()
+            bounds = sample_ranges(n_local)
+            return [local_subsample(np.random.choice(n_glob, size=int(self.hvp_subsample * n_glob)), bounds, eng.rank)
+                    for _ in range(iters)]
         return np.stack([np.random.choice(n_local, size=int(self.hvp_subsample * n_local))
                          for _ in range(iters)]).astype(np.int32)
 
     def _normalize_inputs(self, eng, paths):
         """npg_cg.py:101-107: running average of the observation moments into policy.model ONLY (old_model keeps
         the stale transform -- reproduced literally)."""
-        if eng.world_size > 1:
-            raise NotImplementedError("input_normalization with world_size > 1")
         obs = np.concatenate([p["observations"] for p in paths])
         m = self.policy.model
         a = self.input_normalization
-        in_shift = a * m.in_shift.numpy() + (1 - a) * np.mean(obs, axis=0)
-        in_scale = a * m.in_scale.numpy() + (1 - a) * np.std(obs, axis=0)
+        if eng.world_size > 1:
+            # moments over ALL ranks' samples (two all-reduced passes, like numpy's mean / population std)
+            from mjrl_b200.parallel import allreduce_sum_host
+            n_glob = float(eng.n_global())
+            mean = allreduce_sum_host(obs.sum(axis=0), eng.cfg.device) / n_glob
+            std = np.sqrt(allreduce_sum_host(((obs - mean) ** 2).sum(axis=0), eng.cfg.device) / n_glob)
+        else:
+            mean, std = np.mean(obs, axis=0), np.std(obs, axis=0)
+        in_shift = a * m.in_shift.numpy() + (1 - a) * mean
+        in_scale = a * m.in_scale.numpy() + (1 - a) * std
         m.set_transformations(in_shift, in_scale, m.out_shift.numpy(), m.out_scale.numpy())
         self._pushed = None
         self._push_policy(eng)

@@ -133,6 +133,7 @@ struct mjb_engine {
         std::vector<cudaEvent_t> ev;              // 2 per iteration: around the FVP tile kernel
     };
     std::vector<CgGraph> cg_graphs;
+    std::vector<long long> hvp_len;               // per-iteration subsample lengths of the NEXT cg / step call (ragged, multi-GPU)
     bool graphs_on = true;
     const CgGraph* last_cg_graph = nullptr;       // set when the last CG ran as a graph (its events time the FVP launches)
     cudaEvent_t fit_ev[2] = {nullptr, nullptr};     // around the sequential Adam kernels of the last fit (on its stream)
@@ -402,13 +403,14 @@ int vpg_device(mjb_engine* e, int include_demo, double demo_lam, double* surr) {
 // The launches of one cg_solve (utils/cg_solve.py:3-22): init, then per iteration {tangent prep, FVP tile kernel,
 // partial reduce, all-reduce, fused update (which also emits the next tangent's scale)}.
 int cg_body(mjb_engine* e, const float* b, int iters, float damping, float tol, const int* idx_dev, long long n_idx,
-            const std::vector<cudaEvent_t>* evs) {
+            const std::vector<cudaEvent_t>* evs, const std::vector<long long>* len_each = nullptr) {
     const bool tc = e->tc_ok && e->tc_on;
     launch_cg_init(b, e->x, e->r, e->p, e->d, e->dsc + DS_CG, tc ? e->tc_vscale : nullptr, e->stream);
     e->launches += 1;
     for (int i = 0; i < iters; ++i) {
         const int* idx = idx_dev ? idx_dev + (size_t)i * n_idx : nullptr;
-        if (fvp_device(e, e->p, idx, n_idx, e->Fp, tc, evs ? (*evs)[2 * i] : nullptr, evs ? (*evs)[2 * i + 1] : nullptr)) return -1;
+        const long long n_i = (idx && len_each) ? (*len_each)[i] : n_idx;      // rows of iteration i ([i][0 .. n_i) of the index block)
+        if (fvp_device(e, e->p, idx, n_i, e->Fp, tc, evs ? (*evs)[2 * i] : nullptr, evs ? (*evs)[2 * i + 1] : nullptr)) return -1;
         launch_cg_update(e->Fp, damping, tol, e->x, e->r, e->p, e->d, e->dsc + DS_CG, tc ? e->tc_vscale : nullptr, e->stream);
         e->launches += 1;
     }
@@ -420,6 +422,14 @@ int cg_body(mjb_engine* e, const float* b, int iters, float damping, float tol, 
 // once per distinct shape and replayed; anything that prevents the capture falls back to plain stream launches.
 int cg_device(mjb_engine* e, const float* b, int iters, float damping, float tol, const int* idx_dev, long long n_idx) {
     e->last_cg_graph = nullptr;
+    if (idx_dev && !e->hvp_len.empty()) {                     // ragged per-iteration subsamples: plain stream launches
+        std::vector<long long> len = std::move(e->hvp_len);
+        e->hvp_len.clear();
+        if ((int)len.size() != iters) FAIL(e, "mjb_policy_set_hvp_lengths: one length per CG iteration expected");
+        for (long long l : len) if (l < 0 || l > n_idx) FAIL(e, "mjb_policy_set_hvp_lengths: length exceeds the index block stride");
+        return cg_body(e, b, iters, damping, tol, idx_dev, n_idx, nullptr, &len);
+    }
+    e->hvp_len.clear();
     if (!e->graphs_on || iters < 1) return cg_body(e, b, iters, damping, tol, idx_dev, n_idx, nullptr);
     const long long n = idx_dev ? n_idx : e->n_roll;
     const int sms = e->num_sms - (e->fit_in_flight ? e->vf_sms : 0);
@@ -983,7 +993,7 @@ int mjb_policy_cg(mjb_engine* e, const float* b, int iters, float damping, float
     const int* idx_dev = nullptr;
     if (idx) {
         if (upload_idx(e, idx, (long long)iters * n_idx)) return -1;
-        if (set_subsample_scale(e, n_idx)) return -1;
+        if (set_subsample_scale(e, e->hvp_len.empty() ? n_idx : e->hvp_len[0])) return -1;
         idx_dev = e->idx_dev;
     }
     if (cg_device(e, e->g, iters, damping, residual_tol, idx_dev, n_idx)) return -1;
@@ -1003,7 +1013,7 @@ int mjb_policy_step(mjb_engine* e, int algo, double step_size_or_kl, double cons
     const int* idx_dev = nullptr;
     if (hvp_idx) {
         if (upload_idx(e, hvp_idx, (long long)cg_iters * n_idx)) return -1;
-        if (set_subsample_scale(e, n_idx)) return -1;
+        if (set_subsample_scale(e, e->hvp_len.empty() ? n_idx : e->hvp_len[0])) return -1;
         idx_dev = e->idx_dev;
     }
     if (cg_device(e, e->g, cg_iters, damping, 1e-10f, idx_dev, n_idx)) return -1;
@@ -1079,6 +1089,12 @@ int mjb_policy_step(mjb_engine* e, int algo, double step_size_or_kl, double cons
         e->last_fvp_ms = ms;
     }
     if (out) *out = st;
+    return 0;
+}
+
+int mjb_policy_set_hvp_lengths(mjb_engine* e, const int64_t* n_each, int iters) {
+    e->hvp_len.clear();
+    if (n_each) for (int i = 0; i < iters; ++i) e->hvp_len.push_back((long long)n_each[i]);
     return 0;
 }
 

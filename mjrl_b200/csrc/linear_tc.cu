@@ -427,9 +427,13 @@ __global__ void __launch_bounds__(T_THREADS, 1) linear_tc_tma_kernel(const LinTm
 
     if (warp == TW_CONV) {
         // =============================== TMA producer ===============================
-        if (lane == 0) {
-            mbar_expect_tx(&bars[B_V], (uint32_t)v_bytes);
-            bulk_g2s(smem + a.off_v, a.T + GL_V, (uint32_t)v_bytes, &bars[B_V]);
+        // lane 0 arms the slot's barrier, then lanes 0..15 each issue ONE row copy of the chunk: a single thread needs
+        // ~135 cycles per cp.async.bulk (measured: 8.7 k cycles per 64-row tile, the bound of the first version)
+        {
+            if (lane == 0) {
+                mbar_expect_tx(&bars[B_V], (uint32_t)v_bytes);
+                bulk_g2s(smem + a.off_v, a.T + GL_V, (uint32_t)v_bytes, &bars[B_V]);
+            }
             long long cc = 0;                                          // chunks issued by this CTA
             const uint32_t row_bytes = (uint32_t)K0 * 4u;
             unsigned long long p_wait = 0, p_issue = 0;
@@ -439,22 +443,21 @@ __global__ void __launch_bounds__(T_THREADS, 1) linear_tc_tma_kernel(const LinTm
                 for (int c = 0; c < LM / CHUNK_ROWS; ++c, ++cc) {
                     const int slot = (int)(cc % S);
                     if (cc >= S) mbar_wait(&bars[B_EMPTY + slot], (uint32_t)(((cc / S) - 1) & 1));
-                    TMA_PROF(p_wait);
+                    if (lane == 0) TMA_PROF(p_wait);
                     const long long row0 = tile * LM + (long long)c * CHUNK_ROWS;
                     const int rows = (int)max(0LL, min((long long)CHUNK_ROWS, a.n - row0));
-                    if (rows > 0) {
-                        mbar_expect_tx(&bars[B_FULL + slot], row_bytes * (uint32_t)rows);
-                        unsigned char* dst = smem + a.off_ring + (size_t)slot * chunk_bytes;
-                        const float* src = a.obs + row0 * K0;
-                        for (int r = 0; r < rows; ++r)
-                            bulk_g2s(dst + (size_t)r * pitch * 4, src + (size_t)r * K0, row_bytes, &bars[B_FULL + slot]);
-                    } else {
-                        mbar_arrive(&bars[B_FULL + slot]);             // nothing to load: complete the phase by hand
+                    if (lane == 0) {
+                        if (rows > 0) mbar_expect_tx(&bars[B_FULL + slot], row_bytes * (uint32_t)rows);
+                        else mbar_arrive(&bars[B_FULL + slot]);        // nothing to load: complete the phase by hand
                     }
-                    TMA_PROF(p_issue);
+                    __syncwarp();                                      // the barrier is armed before any copy can complete
+                    if (lane < rows)
+                        bulk_g2s(smem + a.off_ring + (size_t)slot * chunk_bytes + (size_t)lane * pitch * 4,
+                                 a.obs + (row0 + lane) * K0, row_bytes, &bars[B_FULL + slot]);
+                    if (lane == 0) TMA_PROF(p_issue);
                 }
             }
-            if (a.prof) { atomicAdd(a.prof + 9, p_wait); atomicAdd(a.prof + 10, p_issue); }
+            if (a.prof && lane == 0) { atomicAdd(a.prof + 9, p_wait); atomicAdd(a.prof + 10, p_issue); }
         }
     } else if (warp == TW_CONV + 1) {
         // =============================== MMA issuer ===============================
@@ -552,7 +555,9 @@ __global__ void __launch_bounds__(T_THREADS, 1) linear_tc_tma_kernel(const LinTm
                 mbar_wait(&bars[B_FULL + slot], (uint32_t)((cc / S) & 1));
                 CV_PROF(c_wf);
                 const float* raw = reinterpret_cast<const float*>(smem + a.off_ring + (size_t)slot * chunk_bytes);
-                for (int u = 0; u < NFB_; ++u) {
+#pragma unroll
+                for (int u = 0; u < NFB; ++u) {
+                    if (u >= NFB_) break;
                     const int wi = warp + TW_CONV * u;
                     const int rg = wi & 1, cb = wi >> 1;             // row group of the slot, 16-feature column block
                     const int rl = 8 * rg + r8;                      // row inside the slot

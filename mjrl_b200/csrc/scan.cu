@@ -4,8 +4,8 @@
 //   whitening                        algos/batch_reinforce.py:185
 // The recurrences y_t = x_t + g*y_{t+1} are evaluated *sequentially per path in fp64 with separate
 // multiply and add* (no FMA contraction), i.e. in exactly the reference's operation order, so returns and
-// advantages are bit-identical to numpy given the same inputs.  Parallelism is across paths: one thread per
-// path; a warp's 32 paths each stream their own 128-byte lines, which stay L1-resident for 16 steps.
+// advantages are bit-identical to numpy given the same inputs.  Parallelism is across paths (lane = path); the data
+// moves through shared-memory tiles with coalesced 256-byte segments (see "tiled, coalesced scans" below).
 #include "kernels.h"
 
 namespace mjb {
@@ -32,16 +32,71 @@ void launch_tstep(const int* path_off, int n_paths, int* tstep, cudaStream_t s) 
     tstep_kernel<<<min(n_paths, 148 * 8), 128, 0, s>>>(path_off, n_paths, tstep);
 }
 
+// ---- tiled, coalesced scans ------------------------------------------------------------------------------------------
+// One warp owns 32 consecutive paths (lane = path) and walks them backwards in chunks of 32 steps.  A chunk is staged
+// through shared memory: for every path the 32 lanes load its 32 consecutive doubles (one coalesced 256-byte segment),
+// lane j then runs path j's recurrence over the staged row -- sequentially, fp64, separate multiply and add, i.e. the
+// reference's operation order -- and the results leave through the same tile with coalesced stores.  The loads of the
+// NEXT chunk are issued into registers before the recurrence runs, so their latency hides under the dependent chain
+// (32 steps x DMUL+DADD).  The chain itself is the floor: bit-exact parity forbids re-associating it, so a path costs
+// T x ~20 cycles no matter how it is fed -- coalescing removes the 32-byte-sector waste of one-thread-per-path loads
+// (16 MB in 167 us before), it cannot beat the recurrence (1000 steps ~ 10 us; a batch of few very long paths stays
+// serial in its paths).
+constexpr int SC = 32;                       // steps per staged chunk
+constexpr unsigned FULL = 0xffffffffu;
+
+// ragged geometry of lane `lane`'s own path and of path j of this warp (broadcast)
+struct WarpPaths {
+    int o, T, nchunk;
+    __device__ __forceinline__ void init(const int* __restrict__ path_off, int n_paths, int p) {
+        o = p < n_paths ? path_off[p] : 0;
+        T = p < n_paths ? path_off[p + 1] - o : 0;
+        int tm = T;
+        for (int d = 16; d > 0; d >>= 1) tm = max(tm, __shfl_xor_sync(FULL, tm, d));
+        nchunk = (tm + SC - 1) / SC;
+    }
+};
+
 // returns: reverse scan y_t = r_t + gamma*y_{t+1}
-__global__ void returns_kernel(const double* __restrict__ rew, const int* __restrict__ path_off, int n_paths,
-                               double gamma, double* __restrict__ ret) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_paths) return;
-    const int o = path_off[p], T = path_off[p + 1] - o;
+__global__ void __launch_bounds__(32) returns_kernel(const double* __restrict__ rew, const int* __restrict__ path_off,
+                                                     int n_paths, double gamma, double* __restrict__ ret) {
+    __shared__ double tile[32][SC + 1];
+    const int lane = threadIdx.x;
+    WarpPaths w;
+    w.init(path_off, n_paths, blockIdx.x * 32 + lane);
+    // chunk c of path j covers steps [T_j - (c+1) SC, T_j - c SC) clipped at 0; lane l holds step T_j - (c+1) SC + l
+    auto load_chunk = [&](int c, double (&buf)[32]) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int oj = __shfl_sync(FULL, w.o, j), Tj = __shfl_sync(FULL, w.T, j);
+            const int t = Tj - (c + 1) * SC + lane;
+            buf[j] = (t >= 0 && Tj - c * SC > 0) ? rew[oj + t] : 0.0;
+        }
+    };
+    double buf[32];
+    if (w.nchunk > 0) load_chunk(0, buf);
     double run = 0.0;
-    for (int t = T - 1; t >= 0; --t) {
-        run = __dadd_rn(rew[o + t], __dmul_rn(gamma, run));
-        ret[o + t] = run;
+    for (int c = 0; c < w.nchunk; ++c) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tile[j][lane] = buf[j];
+        __syncwarp();
+        if (c + 1 < w.nchunk) load_chunk(c + 1, buf);            // in flight under the recurrence below
+        const int hi = w.T - c * SC;
+        if (hi > 0) {
+            const int first = max(SC - hi, 0);                    // tile index of step 0 when the chunk is clipped
+            for (int k = SC - 1; k >= first; --k) {
+                run = __dadd_rn(tile[lane][k], __dmul_rn(gamma, run));
+                tile[lane][k] = run;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int oj = __shfl_sync(FULL, w.o, j), Tj = __shfl_sync(FULL, w.T, j);
+            const int t = Tj - (c + 1) * SC + lane;
+            if (t >= 0 && Tj - c * SC > 0) ret[oj + t] = tile[j][lane];
+        }
+        __syncwarp();
     }
 }
 void launch_returns(const double* rew, const int* path_off, int n_paths, double gamma, double* ret, cudaStream_t s) {
@@ -49,46 +104,85 @@ void launch_returns(const double* rew, const int* path_off, int n_paths, double 
     returns_kernel<<<(n_paths + 31) / 32, 32, 0, s>>>(rew, path_off, n_paths, gamma, ret);
 }
 
-// per-path undiscounted return: forward sum in Python's sum() order (batch_reinforce.py:188)
-__global__ void path_sums_kernel(const double* __restrict__ rew, const int* __restrict__ path_off, int n_paths,
-                                 double* __restrict__ path_ret) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_paths) return;
-    const int o = path_off[p], T = path_off[p + 1] - o;
+// per-path undiscounted return: forward sum in Python's sum() order (batch_reinforce.py:188), same staging (forward)
+__global__ void __launch_bounds__(32) path_sums_kernel(const double* __restrict__ rew, const int* __restrict__ path_off,
+                                                       int n_paths, double* __restrict__ path_ret) {
+    __shared__ double tile[32][SC + 1];
+    const int lane = threadIdx.x, p = blockIdx.x * 32 + lane;
+    WarpPaths w;
+    w.init(path_off, n_paths, p);
     double tot = 0.0;
-    for (int t = 0; t < T; ++t) tot = __dadd_rn(tot, rew[o + t]);
-    path_ret[p] = tot;
+    for (int c = 0; c < w.nchunk; ++c) {
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+            const int oj = __shfl_sync(FULL, w.o, j), Tj = __shfl_sync(FULL, w.T, j);
+            const int t = c * SC + lane;
+            tile[j][lane] = t < Tj ? rew[oj + t] : 0.0;
+        }
+        __syncwarp();
+        const int cnt = min(SC, w.T - c * SC);
+        for (int k = 0; k < cnt; ++k) tot = __dadd_rn(tot, tile[lane][k]);
+        __syncwarp();
+    }
+    if (p < n_paths) path_ret[p] = tot;
 }
 void launch_path_sums(const double* rew, const int* path_off, int n_paths, double* path_ret, cudaStream_t s) {
     if (n_paths <= 0) return;
     path_sums_kernel<<<(n_paths + 31) / 32, 32, 0, s>>>(rew, path_off, n_paths, path_ret);
 }
 
-__global__ void advantages_kernel(const double* __restrict__ rew, const float* __restrict__ base,
-                                  const double* __restrict__ ret, const int* __restrict__ path_off,
-                                  const unsigned char* __restrict__ terminated, int n_paths, double gamma,
-                                  double gamma_lam, int use_gae, double* __restrict__ adv) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_paths) return;
-    const int o = path_off[p], T = path_off[p + 1] - o;
-    if (T <= 0) return;
-    if (!use_gae) {                                   // returns - baseline (process_samples.py:11-13)
-        for (int t = 0; t < T; ++t) adv[o + t] = __dsub_rn(ret[o + t], (double)base[o + t]);
-        return;
-    }
-    const bool term = terminated[p] != 0;
+// GAE (process_samples.py:7-35) incl. the fp32 / fp64 bootstrap asymmetry (A5, A6); same staging as the returns
+__global__ void __launch_bounds__(32) advantages_kernel(const double* __restrict__ rew, const float* __restrict__ base,
+                                                        const double* __restrict__ ret, const int* __restrict__ path_off,
+                                                        const unsigned char* __restrict__ terminated, int n_paths,
+                                                        double gamma, double gamma_lam, int use_gae,
+                                                        double* __restrict__ adv) {
+    __shared__ double tile[32][SC + 1];
+    __shared__ float tb[32][SC + 1];
+    const int lane = threadIdx.x, p = blockIdx.x * 32 + lane;
+    WarpPaths w;
+    w.init(path_off, n_paths, p);
+    const bool term = p < n_paths ? terminated[p] != 0 : false;
     const float gf = (float)gamma;
     double run = 0.0;
-    float b_next = base[o + T - 1];                   // bootstrap with the last *visited* state (:25)
-    for (int t = T - 1; t >= 0; --t) {
-        const float b = base[o + t];
-        double nxt;
-        if (term) nxt = (t == T - 1) ? __dmul_rn(gamma, 0.0) : __dmul_rn(gamma, (double)b_next);   // b1 promoted to fp64
-        else      nxt = (double)__fmul_rn(gf, b_next);                                             // b1 stays fp32
-        const double td = __dsub_rn(__dadd_rn(rew[o + t], nxt), (double)b);
-        run = __dadd_rn(td, __dmul_rn(gamma_lam, run));
-        adv[o + t] = run;
-        b_next = b;
+    float b_next = w.T > 0 ? base[w.o + w.T - 1] : 0.0f;             // bootstrap with the last *visited* state (:25)
+    for (int c = 0; c < w.nchunk; ++c) {
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+            const int oj = __shfl_sync(FULL, w.o, j), Tj = __shfl_sync(FULL, w.T, j);
+            const int t = Tj - (c + 1) * SC + lane;
+            const bool in = t >= 0 && Tj - c * SC > 0;
+            tile[j][lane] = in ? (use_gae ? rew[oj + t] : ret[oj + t]) : 0.0;
+            tb[j][lane] = in ? base[oj + t] : 0.0f;
+        }
+        __syncwarp();
+        const int hi = w.T - c * SC;
+        if (hi > 0) {
+            const int first = max(SC - hi, 0);
+            for (int k = SC - 1; k >= first; --k) {
+                const float b = tb[lane][k];
+                if (!use_gae) {                                       // returns - baseline (process_samples.py:11-13)
+                    tile[lane][k] = __dsub_rn(tile[lane][k], (double)b);
+                    continue;
+                }
+                const bool last = (c == 0 && k == SC - 1);           // t == T - 1
+                double nxt;
+                if (term) nxt = last ? __dmul_rn(gamma, 0.0) : __dmul_rn(gamma, (double)b_next);   // b1 promoted to fp64
+                else      nxt = (double)__fmul_rn(gf, b_next);                                     // b1 stays fp32
+                const double td = __dsub_rn(__dadd_rn(tile[lane][k], nxt), (double)b);
+                run = __dadd_rn(td, __dmul_rn(gamma_lam, run));
+                tile[lane][k] = run;
+                b_next = b;
+            }
+        }
+        __syncwarp();
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+            const int oj = __shfl_sync(FULL, w.o, j), Tj = __shfl_sync(FULL, w.T, j);
+            const int t = Tj - (c + 1) * SC + lane;
+            if (t >= 0 && Tj - c * SC > 0) adv[oj + t] = tile[j][lane];
+        }
+        __syncwarp();
     }
 }
 void launch_advantages(const double* rew, const float* base, const double* ret, const int* path_off,

@@ -71,35 +71,21 @@ struct TcFitArgs {
     long long* prof;
 };
 
-struct AdamP { float one_m_b1, b2, one_m_b2, rbc2_sqrt, eps, neg_step, reg, cinv, neg_ec; };
+struct AdamP { float one_m_b1, b2, one_m_b2, rbc2_sqrt, eps, neg_step, reg; };
 
-// torch.optim.Adam update: w -= step * m / (sqrt(v) / sqrt(1 - b2^t) + eps).  One SM updates all 20 k parameters every
-// step and the MUFU unit (16 results / clock / SM) is what bounds that, so the quotient costs ONE MUFU op, not two:
-//   r = rsqrt(v),  1 / (sqrt(v) c + eps) = (r / c) / (1 + q),  q = eps r / c,  1 / (1 + q) = 1 - q + q^2 - q^3 + O(q^4)
-// with the series on the FMA pipe.  q is ~1e-4 .. 1e-3 for every parameter that sees a gradient; lanes with q > 0.01
-// (error 1e-8 at the threshold), v == 0 or a non-finite r take the two-MUFU form sqrt + rcp.  Either way the error is
-// <= 2 ulp, the same order as the two-term fp16 rounding of the GEMM operands.
-__device__ __forceinline__ float adam_inv_slow(float v, const AdamP& c) {
-    float sq, rc;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(v));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fmaf(sq, c.rbc2_sqrt, c.eps)));
-    return rc;
-}
+// torch.optim.Adam update.  One SM updates all 20 k parameters every step, so the square root and the division use
+// the MUFU approximations (<= 2 ulp each, the same order as the two-term fp16 rounding of the GEMM operands).  The update
+// is MUFU-bound (16 results / clock / SM: ~1000 cycles per half of W2); a one-MUFU variant (rsqrt + series for the eps
+// term, exact fallback under a branch) was measured SLOWER -- 2400 cycles per half -- because the branch keeps ptxas
+// from interleaving the eight independent parameter pairs of a chunk.
 __device__ __forceinline__ float adam_apply(float g, float w, float& m, float& v, const AdamP& c) {
     g = fmaf(c.reg, w, g);
     m = fmaf(c.one_m_b1, g - m, m);
     v = fmaf(c.one_m_b2 * g, g, v * c.b2);
-    float r;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-    const float nq = r * c.neg_ec;                                   // -q
-    float inv;
-    if (nq >= -0.01f) {
-        const float p = fmaf(nq, fmaf(nq, 1.0f + nq, 1.0f), 1.0f);   // 1 - q + q^2 - q^3
-        inv = (r * c.cinv) * p;
-    } else {
-        inv = adam_inv_slow(v, c);
-    }
-    return fmaf(c.neg_step, m * inv, w);
+    float sq, rc;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(v));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(fmaf(sq, c.rbc2_sqrt, c.eps)));
+    return fmaf(c.neg_step, m * rc, w);
 }
 
 // ---- packed fp32x2 arithmetic (sm_100 FFMA2 / FMUL2 / FADD2): two IEEE-rounded lanes per instruction, bit-identical to
@@ -111,11 +97,11 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm(
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
-struct AdamP2 { f32x2 one_m_b1, b2, one_m_b2, neg_step, reg, gscale, cinv, neg_ec, one; };
+struct AdamP2 { f32x2 one_m_b1, b2, one_m_b2, rbc2_sqrt, eps, neg_step, reg, gscale; };
 
 // two parameters at once; same operation sequence as adam_apply (so the results are bit-identical)
 __device__ __forceinline__ void adam_apply2(float g0, float g1, float& w0, float& w1, float& m0, float& m1, float& v0, float& v1,
-                                            const AdamP2& c, const AdamP& cs) {
+                                            const AdamP2& c) {
     const f32x2 w = pk2(w0, w1);
     f32x2 m = pk2(m0, m1), v = pk2(v0, v1);
     f32x2 g = mul2(pk2(g0, g1), c.gscale);
@@ -123,21 +109,14 @@ __device__ __forceinline__ void adam_apply2(float g0, float g1, float& w0, float
     m = fma2(c.one_m_b1, sub2(g, m), m);
     v = fma2(mul2(c.one_m_b2, g), g, mul2(v, c.b2));
     upk2(v, v0, v1);
-    float r0, r1;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(v0));
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(v1));
-    const f32x2 r = pk2(r0, r1);
-    const f32x2 nq = mul2(r, c.neg_ec);                              // -q (both lanes)
-    float nq0, nq1;
-    upk2(nq, nq0, nq1);
-    f32x2 inv;
-    if (nq0 >= -0.01f && nq1 >= -0.01f) {                            // (NaN / inf fail the comparison -> slow path)
-        const f32x2 p = fma2(nq, fma2(nq, fma2(nq, c.one, c.one), c.one), c.one);     // 1 - q + q^2 - q^3
-        inv = mul2(mul2(r, c.cinv), p);
-    } else {
-        inv = pk2(adam_inv_slow(v0, cs), adam_inv_slow(v1, cs));
-    }
-    upk2(fma2(c.neg_step, mul2(m, inv), w), w0, w1);
+    float s0, s1, r0, r1;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s0) : "f"(v0));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s1) : "f"(v1));
+    float d0, d1;
+    upk2(fma2(pk2(s0, s1), c.rbc2_sqrt, c.eps), d0, d1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
+    upk2(fma2(c.neg_step, mul2(m, pk2(r0, r1)), w), w0, w1);
     upk2(m, m0, m1);
 }
 
@@ -308,13 +287,13 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
     ap.one_m_b1 = 1.0f - a.beta1; ap.b2 = a.beta2; ap.one_m_b2 = 1.0f - a.beta2; ap.eps = a.eps; ap.reg = a.reg;
     AdamP2 ap2;
     ap2.one_m_b1 = pk2(ap.one_m_b1, ap.one_m_b1); ap2.b2 = pk2(ap.b2, ap.b2); ap2.one_m_b2 = pk2(ap.one_m_b2, ap.one_m_b2);
-    ap2.reg = pk2(ap.reg, ap.reg); ap2.gscale = pk2(1.0f / (SG * SA), 1.0f / (SG * SA));
-    ap2.one = pk2(1.0f, 1.0f);
-    ap2.neg_step = ap2.cinv = ap2.neg_ec = 0;
-    ap.rbc2_sqrt = ap.neg_step = ap.cinv = ap.neg_ec = 0.0f;
+    ap2.eps = pk2(ap.eps, ap.eps); ap2.reg = pk2(ap.reg, ap.reg); ap2.gscale = pk2(1.0f / (SG * SA), 1.0f / (SG * SA));
+    ap2.rbc2_sqrt = ap2.neg_step = 0;
+    ap.rbc2_sqrt = ap.neg_step = 0.0f;
 
     for (int s = 0; s < a.steps; ++s) {
         sync_ops();                                                  // X(s), weights(s) staged
+        TC_PROF(13);                                                 // (barrier skew at the top of the step)
         if (tid == 0) {                                              // layer 1: z1^T = W1 x^T
             tcgen05_fence_after();
             const uint32_t xb = sbase + ((s & 1) ? S_X2 : S_XH);
@@ -322,13 +301,14 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
                            xb, xb + X_BYTES, 2 * LB64, LB64, 128, ID_L1);
             mma_commit(&bars[0]);
         }
+        TC_PROF(14);                                                 // (issue of the six layer-1 MMAs)
         if (s + 1 < a.steps) load_rows(i1);                          // rows of step s+1: a whole step to land
         i1 = i2;
         if (s + 3 < a.steps) i2 = a.perm[(size_t)(s + 3) * NB + gn];
         const float4 cst = cst_next;
         if (s + 1 < a.steps) cst_next = a.consts[s + 1];
-        ap.rbc2_sqrt = cst.x; ap.neg_step = cst.y; ap.cinv = cst.z; ap.neg_ec = cst.w;
-        ap2.neg_step = pk2(cst.y, cst.y); ap2.cinv = pk2(cst.z, cst.z); ap2.neg_ec = pk2(cst.w, cst.w);
+        ap.rbc2_sqrt = cst.x; ap.neg_step = cst.y;
+        ap2.rbc2_sqrt = pk2(cst.x, cst.x); ap2.neg_step = pk2(cst.y, cst.y);
         TC_PROF(0);
         wait0();
         TC_PROF(1);
@@ -475,7 +455,7 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
             for (int j = 0; j < 16; j += 2) {
                 float m0 = __uint_as_float(mm[j]), m1 = __uint_as_float(mm[j + 1]);
                 float v0 = __uint_as_float(vv[j]), v1 = __uint_as_float(vv[j + 1]);
-                adam_apply2(__uint_as_float(g[j]), __uint_as_float(g[j + 1]), w2[16 * c16 + j], w2[16 * c16 + j + 1], m0, m1, v0, v1, ap2, ap);
+                adam_apply2(__uint_as_float(g[j]), __uint_as_float(g[j + 1]), w2[16 * c16 + j], w2[16 * c16 + j + 1], m0, m1, v0, v1, ap2);
                 mm[j] = __float_as_uint(m0); mm[j + 1] = __float_as_uint(m1);
                 vv[j] = __float_as_uint(v0); vv[j + 1] = __float_as_uint(v1);
             }

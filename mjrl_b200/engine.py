@@ -247,6 +247,14 @@ class Engine:
     def step(self, algo="npg", step_size=0.01, const_learn_rate=None, cg_iters=10, damping=1e-4, demo_lam=0.0,
              hvp_idx=None):
         st = StepStats()
+        if isinstance(hvp_idx, (list, tuple)):               # ragged per-iteration lists (data-parallel subsample)
+            lens = np.array([len(r) for r in hvp_idx], dtype=np.int64)
+            stride = max(1, int(lens.max()))
+            block = np.zeros((cg_iters, stride), dtype=np.int32)
+            for i, r in enumerate(hvp_idx):
+                block[i, :len(r)] = r
+            self._ck(self.lib.mjb_policy_set_hvp_lengths(self.h, _ptr(lens), int(cg_iters)), "set_hvp_lengths")
+            hvp_idx = block
         ii = None if hvp_idx is None else np.ascontiguousarray(hvp_idx, dtype=np.int32).reshape(cg_iters, -1)
         self._ck(self.lib.mjb_policy_step(self.h, ALGO[algo], float(step_size),
                                           -1.0 if const_learn_rate is None else float(const_learn_rate),

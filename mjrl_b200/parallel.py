@@ -51,3 +51,29 @@ def local_subsample(global_idx, bounds_samples, rank):
     idx = np.asarray(global_idx)
     keep = idx[(idx >= lo) & (idx < hi)] - lo
     return keep.astype(np.int32)
+
+
+def sample_ranges(n_local):
+    """[lo, hi) global row range of every rank, from the ranks' local sample counts (rank order = global sample order)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    t = torch.zeros(world, dtype=torch.int64)
+    t[dist.get_rank()] = int(n_local)
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t)
+    cnt = t.cpu().numpy()
+    hi = np.cumsum(cnt)
+    return [(int(h - c), int(h)) for c, h in zip(cnt, hi)]
+
+
+def allreduce_sum_host(x, device=None):
+    """Sum a small float64 host array over the ranks (default torch.distributed group)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64).copy())
+    if dist.get_backend() == "nccl":
+        t = t.cuda(device)
+    dist.all_reduce(t)
+    return t.cpu().numpy()

@@ -66,7 +66,63 @@ def main():
         eng.close()
         if rank == 0:
             print("multigpu ok:", case, "world", world, flush=True)
+    agents_section(rank, world)
     dist.destroy_process_group()
+
+
+def agents_section(rank, world):
+    """The drop-in classes under data parallelism: every rank runs the same program on its shard of the
+    trajectories; hvp_sample_frac < 1 (global index draws, each rank keeps its range), DAPG (demonstrations sharded like
+    the rollouts) and input_normalization (all-reduced observation moments) must reproduce the single-process fixtures."""
+    from mjrl_b200 import runtime
+    from mjrl_b200.algos.dapg import DAPG
+    from mjrl_b200.algos.npg_cg import NPG
+    from mjrl_b200.baselines.mlp_baseline import MLPBaseline
+    from mjrl_b200.policies.gaussian_mlp import MLP
+    from mjrl_b200.utils.gym_env import EnvSpec
+    g = load_golden("swim_40x250")
+    m = g["meta"]
+    paths = golden_paths(g)
+    for p, a in zip(paths, np.split(g["advantages"], np.cumsum(g["path_len"])[:-1])):
+        p["advantages"] = a
+    lens = [len(p["rewards"]) for p in paths]
+    s, e = shard_bounds(lens, world)[rank]
+    mine = paths[s:e]
+    es = EnvSpec(m["obs_dim"], m["act_dim"], m["horizon"])
+    kw = dict(FIM_invert_args={"iters": m["cg_iters"], "damping": m["damping"]})
+
+    def fresh():
+        pol = MLP(es, hidden_sizes=m["hidden"], seed=m["policy_seed"])
+        bl = MLPBaseline(es, reg_coef=1e-3, batch_size=64, epochs=2, learn_rate=1e-3)
+        bl.set_flat_weights(g["vf_w0"])
+        return pol, bl
+
+    th0 = g["theta0"]
+    # ---- hvp_sample_frac = 0.5: the fixture drew its index sets from np.random.seed(77) ----
+    pol, bl = fresh()
+    agent = NPG(None, pol, bl, normalized_step_size=m["npg_step"], hvp_sample_frac=0.5, **kw)
+    np.random.seed(77)
+    agent.train_from_paths(mine)
+    assert one_minus_cos(pol.get_param_values() - th0, g["sub_theta"] - th0) < 1e-4
+    # ---- DAPG: every rank is given the SAME demonstration list and keeps its shard ----
+    pol, bl = fresh()
+    demo = golden_paths(g, demo=True)
+    agent = DAPG(None, pol, bl, demo_paths=demo, kl_dist=0.01, lam_0=1.0, lam_1=0.95, **kw)
+    agent.iter_count = 3.0
+    agent.train_from_paths(mine)
+    assert one_minus_cos(pol.get_param_values() - th0, g["dapg_theta"] - th0) < 1e-4
+    assert abs(agent.last_step.alpha / g["dapg_alpha"] - 1) < 2e-3
+    # ---- input_normalization: observation moments over ALL ranks' samples ----
+    gi = load_golden("inorm_swim_40x250")
+    pol, bl = fresh()
+    agent = NPG(None, pol, bl, normalized_step_size=m["npg_step"], input_normalization=gi["meta"]["input_normalization"], **kw)
+    agent.train_from_paths(mine)
+    for k in ("in_shift", "in_scale"):
+        np.testing.assert_allclose(getattr(pol.model, k).numpy(), gi["new_" + k], rtol=1e-5, atol=1e-6)
+    assert one_minus_cos(pol.get_param_values() - th0, gi["theta1"] - th0) < 1e-4
+    runtime.shutdown()
+    if rank == 0:
+        print("multigpu agents ok: world", world, flush=True)
 
 
 if __name__ == "__main__":

@@ -18,3 +18,4 @@ def test_two_rank_shard_invariance(cuda_device):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("multigpu ok") == 3
+    assert r.stdout.count("multigpu agents ok") == 1

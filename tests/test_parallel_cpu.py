@@ -91,6 +91,30 @@ def _worker(rank, world, port, out):
         dist.all_reduce(tf)
         f_full = O.fvp(spec, theta, cat(paths, "observations"), v, 0.0)
         assert np.linalg.norm(tf.numpy() - f_full) / np.linalg.norm(f_full) < 1e-10
+        # ---- hvp_sample_frac < 1 (npg_cg.py:65-69): every rank draws the SAME global indices and keeps its own range;
+        #      the union of the local lists is the reference's subsample, the all-reduced product equals the gathered one
+        from mjrl_b200.parallel import allreduce_sum_host, sample_ranges
+        ranges = sample_ranges(n_loc)
+        assert ranges[rank] == (off, off + n_loc) and ranges[-1][1] == n_glob
+        gidx = np.random.RandomState(9).choice(n_glob, size=n_glob // 2)
+        lidx = local_subsample(gidx, ranges, rank)
+        cnt = allreduce_sum_host(np.array([float(len(lidx))]))
+        assert int(cnt[0]) == len(gidx)
+        f_sub = O.fvp(spec, theta, cat(mine, "observations")[lidx], v, 0.0)
+        f_sub[:-act_dim] *= len(lidx) / len(gidx)
+        f_sub[-act_dim:] /= world
+        f_sub_full = O.fvp(spec, theta, cat(paths, "observations")[gidx], v, 0.0)
+        assert np.linalg.norm(allreduce_sum_host(f_sub) - f_sub_full) / np.linalg.norm(f_sub_full) < 1e-10
+        # ---- input_normalization moments (npg_cg.py:101-107) over all ranks' samples, two all-reduced passes
+        obs_loc, obs_all = cat(mine, "observations"), cat(paths, "observations")
+        mean_o = allreduce_sum_host(obs_loc.sum(axis=0)) / n_glob
+        std_o = np.sqrt(allreduce_sum_host(((obs_loc - mean_o) ** 2).sum(axis=0)) / n_glob)
+        assert np.allclose(mean_o, obs_all.mean(axis=0), rtol=0, atol=1e-12) and np.allclose(std_o, obs_all.std(axis=0), rtol=0, atol=1e-12)
+        # ---- DAPG demonstrations are sharded like the rollouts: every demo path lands on exactly one rank
+        demo = O.synthetic_paths(obs_dim, act_dim, 3, 40, seed=8)
+        owned = allreduce_sum_host(np.array([float(sum(len(p["rewards"]) for p in shard_paths(demo, world, rank)))]))
+        assert int(owned[0]) == sum(len(p["rewards"]) for p in demo)
+        assert shard_bounds([7], 2) == [(0, 1), (1, 1)]           # fewer paths than ranks: the last ranks stay empty
         out.put((rank, "ok"))
     except Exception as exc:      # surface the failure in the parent
         out.put((rank, repr(exc)))

@@ -30,8 +30,9 @@ for cl, mp in ((1, True),):
     out = (C.c_longlong * 16)()
     eng.lib.mjb_dev_vf_profile(eng.h, out, 0)
     steps = N // 64 - 1
-    tot = sum(out[:13])
+    tot = sum(out[:15])
     print("vf_fit_tc_kernel: %.2f us/step wall, %d cycles/step" % (dt / steps * 1e6, tot // steps))
+    names = names_tc + ["(top-of-step barrier: waiting for the slowest warp)", "(issue of the 6 layer-1 MMAs; 'issue L1' above is what follows)"]
     for i, n in enumerate(names):
         if n == "-":
             continue
