@@ -867,56 +867,38 @@ int mjb_get_adv_white(mjb_engine* e, float* out) { return d2any(e, out, e->adv_w
 
 int mjb_process_paths(mjb_engine* e, mjb_batch_stats* out) {
     if (!e->have_adv) FAIL(e, "mjb_process_paths: advantages not set");
-    // mean, then population variance about the mean (two passes, like numpy's std)
+    // Everything stays on the device and on the stream: mean, then population variance about the mean (two passes, like
+    // numpy's std), whitening, per-path return statistics; the cross-rank reductions are NCCL calls on the same stream.
+    // ONE host round trip at the end brings the seven scalars back.
+    const double inv_n = 1.0 / (double)e->n_glob_roll, inv_p = 1.0 / (double)e->n_glob_paths;
     launch_moments(e->adv, e->n_roll, nullptr, e->mom_scratch, e->dsc + DS_MOM, e->stream);
     if (allreduce(e, e->dsc + DS_MOM, 2, ncclDouble)) return -1;
-    CK(e, cudaMemcpyAsync(e->h_dsc + DS_MOM, e->dsc + DS_MOM, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    CK(e, cudaStreamSynchronize(e->stream));
-    const double mean = e->h_dsc[DS_MOM] / (double)e->n_glob_roll;
-    e->h_dsc[DS_STATS] = mean;
-    CK(e, cudaMemcpyAsync(e->dsc + DS_STATS, e->h_dsc + DS_STATS, sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    launch_stats_finalize(e->dsc + DS_MOM, inv_n, e->dsc + DS_STATS, 0, e->stream);
     launch_moments(e->adv, e->n_roll, e->dsc + DS_STATS, e->mom_scratch, e->dsc + DS_MOM, e->stream);
     if (allreduce(e, e->dsc + DS_MOM, 2, ncclDouble)) return -1;
-    CK(e, cudaMemcpyAsync(e->h_dsc + DS_MOM, e->dsc + DS_MOM, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    CK(e, cudaStreamSynchronize(e->stream));
-    const double sd = std::sqrt(e->h_dsc[DS_MOM + 1] / (double)e->n_glob_roll);
-    e->h_dsc[DS_STATS + 1] = sd;
-    CK(e, cudaMemcpyAsync(e->dsc + DS_STATS, e->h_dsc + DS_STATS, 2 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    launch_stats_finalize(e->dsc + DS_MOM, inv_n, e->dsc + DS_STATS, 1, e->stream);
     launch_whiten(e->adv, e->n_roll, e->dsc + DS_STATS, e->adv_white, e->stream);
-    e->launches += 5;
     e->have_white = true;
     // path-return statistics (batch_reinforce.py:188-192)
     launch_path_sums(e->rew, e->path_off, e->n_paths, e->path_ret, e->stream);
-    e->launches += 1;
-    std::vector<double> pr((size_t)std::max(1, e->n_paths));
-    CK(e, cudaMemcpyAsync(pr.data(), e->path_ret, sizeof(double) * e->n_paths, cudaMemcpyDeviceToHost, e->stream));
-    e->d2h_bytes += (long long)sizeof(double) * e->n_paths;
-    CK(e, cudaStreamSynchronize(e->stream));
-    double s = 0, mn = INFINITY, mx = -INFINITY;
-    for (int i = 0; i < e->n_paths; ++i) { s += pr[i]; mn = std::min(mn, pr[i]); mx = std::max(mx, pr[i]); }
-    double* h = e->h_dsc + DS_RET;
-    h[0] = s; h[1] = -mn; h[2] = mx;
+    launch_path_stats(e->path_ret, e->n_paths, inv_p, e->dsc + DS_RET, 0, e->stream);
     if (e->comm) {
-        CK(e, cudaMemcpyAsync(e->dsc + DS_RET, h, 3 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
         if (allreduce(e, e->dsc + DS_RET, 1, ncclDouble, ncclSum)) return -1;
         if (allreduce(e, e->dsc + DS_RET + 1, 2, ncclDouble, ncclMax)) return -1;
-        CK(e, cudaMemcpyAsync(h, e->dsc + DS_RET, 3 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-        CK(e, cudaStreamSynchronize(e->stream));
     }
-    const double rmean = h[0] / (double)e->n_glob_paths;
-    double ss = 0;
-    for (int i = 0; i < e->n_paths; ++i) ss += (pr[i] - rmean) * (pr[i] - rmean);
-    h[3] = ss;
-    if (e->comm) {
-        CK(e, cudaMemcpyAsync(e->dsc + DS_RET + 3, h + 3, sizeof(double), cudaMemcpyHostToDevice, e->stream));
-        if (allreduce(e, e->dsc + DS_RET + 3, 1, ncclDouble)) return -1;
-        CK(e, cudaMemcpyAsync(h + 3, e->dsc + DS_RET + 3, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-        CK(e, cudaStreamSynchronize(e->stream));
-    }
+    launch_path_stats(e->path_ret, e->n_paths, inv_p, e->dsc + DS_RET, 1, e->stream);
+    if (allreduce(e, e->dsc + DS_RET + 3, 1, ncclDouble)) return -1;
+    e->launches += 11;
+    CK(e, cudaGetLastError());
     if (out) {
-        out->mean_return = rmean; out->std_return = std::sqrt(h[3] / (double)e->n_glob_paths);
+        CK(e, cudaMemcpyAsync(e->h_dsc + DS_STATS, e->dsc + DS_STATS, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        CK(e, cudaMemcpyAsync(e->h_dsc + DS_RET, e->dsc + DS_RET, 4 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        e->d2h_bytes += 6 * (long long)sizeof(double);
+        CK(e, cudaStreamSynchronize(e->stream));
+        const double* h = e->h_dsc + DS_RET;
+        out->mean_return = h[0] * inv_p; out->std_return = std::sqrt(h[3] * inv_p);
         out->min_return = -h[1]; out->max_return = h[2];
-        out->adv_mean = mean; out->adv_std = sd; out->n_samples_global = e->n_glob_roll;
+        out->adv_mean = e->h_dsc[DS_STATS]; out->adv_std = e->h_dsc[DS_STATS + 1]; out->n_samples_global = e->n_glob_roll;
     }
     return 0;
 }

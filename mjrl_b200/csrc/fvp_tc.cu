@@ -248,25 +248,53 @@ __global__ void __launch_bounds__(512, 1) fvp_tc_kernel(const TcFvpArgs a) {
     };
     float gb3_acc = 0.0f;                                             // thread a < 8: running sum_m dy[m][a]
     const long long n_tiles = (a.n + TM - 1) / TM;
+    // Input staging: a 128 x obs_dim tile is <= 31 x 128 elements = at most 8 per thread.  The (row, feature) of each
+    // slot never changes, so it is decoded once; the raw values of the NEXT tile are fetched into registers while the
+    // current tile computes (their L2 / HBM latency used to sit in front of every tile).
+    constexpr int XS = 8;
+    const int n_el = TM * a.obs_dim;
+    uint32_t x_rk[XS];                                                // row | feature << 8 ; 0xffffffff = unused slot
+    float x_raw[XS];
+#pragma unroll
+    for (int i = 0; i < XS; ++i) {
+        const int f = tid + 512 * i;
+        x_rk[i] = f < n_el ? (uint32_t)(f / a.obs_dim) | ((uint32_t)(f % a.obs_dim) << 8) : 0xffffffffu;
+        x_raw[i] = 0.0f;
+    }
+    auto fetch_tile = [&](long long tile) {
+        const long long base = tile * TM;
+#pragma unroll
+        for (int i = 0; i < XS; ++i) {
+            x_raw[i] = 0.0f;
+            if (x_rk[i] != 0xffffffffu) {
+                const int r = x_rk[i] & 0xff, k = x_rk[i] >> 8;
+                const long long row = base + r;
+                if (row < a.n) {
+                    const long long rr = a.idx ? (long long)a.idx[row] : row;
+                    x_raw[i] = __ldg(a.obs + rr * a.obs_dim + k);
+                }
+            }
+        }
+    };
+    if ((long long)blockIdx.x < n_tiles) fetch_tile(blockIdx.x);
     long long it = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const long long base = tile * TM;
         const bool first = (it % FLUSH_TILES == 0);                  // first tile of an accumulation group
         // ================= P0: stage the input tile (transform, split) =================
-        for (int f = tid; f < TM * a.obs_dim; f += 512) {
-            const int r = f / a.obs_dim, k = f - r * a.obs_dim;
-            const long long row = base + r;
-            float v = 0.0f;
-            if (row < a.n) {
-                const long long rr = a.idx ? (long long)a.idx[row] : row;
-                v = (a.obs[rr * a.obs_dim + k] - a.in_shift[k]) / (a.in_scale[k] + 1e-8f);
+#pragma unroll
+        for (int i = 0; i < XS; ++i) {
+            if (x_rk[i] != 0xffffffffu) {
+                const int r = x_rk[i] & 0xff, k = x_rk[i] >> 8;
+                const float v = (base + r < a.n) ? (x_raw[i] - a.in_shift[k]) / (a.in_scale[k] + 1e-8f) : 0.0f;
+                __half h, l;
+                split16(v, h, l);
+                const uint32_t o = core_offset(r, k, 128);
+                *reinterpret_cast<__half*>(smem + S_XHI + o) = h;
+                *reinterpret_cast<__half*>(smem + S_XLO + o) = l;
             }
-            __half h, l;
-            split16(v, h, l);
-            const uint32_t o = core_offset(r, k, 128);
-            *reinterpret_cast<__half*>(smem + S_XHI + o) = h;
-            *reinterpret_cast<__half*>(smem + S_XLO + o) = l;
         }
+        if (tile + gridDim.x < n_tiles) fetch_tile(tile + gridDim.x);     // next tile: in flight under this tile's phases
         if (it == 0 && tid < 128) *reinterpret_cast<__half*>(smem + S_XHI + core_offset(tid, a.obs_dim, 128)) = __float2half_rn(1.0f);
         fence_proxy_async();
         tcgen05_fence_before();
@@ -274,8 +302,7 @@ __global__ void __launch_bounds__(512, 1) fvp_tc_kernel(const TcFvpArgs a) {
         // ================= P1: z1 = x W1^T -> D1, zd1 = x V1^T -> D2 =================
         if (tid == 0) {
             tcgen05_fence_after();
-            ring_load(0, a.P + G_W1S);
-            ring_load(1, a.T + G_W1S);
+            if (it == 0) { ring_load(0, a.P + G_W1S); ring_load(1, a.T + G_W1S); }   // later tiles: prefetched at the end of P7
             ring_wait(0);
 #pragma unroll
             for (int j = 0; j < 2; ++j)
@@ -289,6 +316,8 @@ __global__ void __launch_bounds__(512, 1) fvp_tc_kernel(const TcFvpArgs a) {
             mma_commit(&bars[0]);
         }
         all_wait_mma();
+        // the ring is idle through the epilogue: the first two weight slices of the next GEMM phase stream in under it
+        if (tid == 0) { ring_load(0, a.P + G_W2S); ring_load(1, a.P + G_W2S + CHUNK); }
         // ================= P2: h1 = tanh(z1+b1) -> P ; hd1 = (1-h1^2)(zd1+c1) -> Q =================
 #pragma unroll 1
         for (int cc = 0; cc < 2; ++cc) {
@@ -313,9 +342,7 @@ __global__ void __launch_bounds__(512, 1) fvp_tc_kernel(const TcFvpArgs a) {
         // ================= P3: z2 = h1 W2^T -> D1 ; zd2 = hd1 W2^T + h1 V2^T -> D2 =================
         if (tid == 0) {
             tcgen05_fence_after();
-            ring_load(0, a.P + G_W2S);
-            ring_load(1, a.P + G_W2S + CHUNK);
-            for (int s = 0; s < 8; ++s) {                             // 4 slices of W2, then 4 slices of V2
+            for (int s = 0; s < 8; ++s) {                             // 4 slices of W2, then 4 slices of V2 (0, 1 prefetched)
                 const int slot = s & 1;
                 ring_wait(slot);
 #pragma unroll
@@ -334,6 +361,7 @@ __global__ void __launch_bounds__(512, 1) fvp_tc_kernel(const TcFvpArgs a) {
             mma_commit(&bars[0]);
         }
         all_wait_mma();
+        if (tid == 0) { ring_load(0, a.P + G_W2TS); ring_load(1, a.P + G_W2TS + CHUNK); }   // for P7, under P4 .. P6
         // ================= P4: h2 -> Q (operand) and back into D1 (fp32); ydot on the CUDA cores; delta_y =================
         {
             float yacc[8];
@@ -440,8 +468,6 @@ __global__ void __launch_bounds__(512, 1) fvp_tc_kernel(const TcFvpArgs a) {
         // ================= P7: dh1 = delta2 W2 -> D2 ; G2[n][k|1] += sum_m delta2[m][n] [h1|1][m][k] =================
         if (tid == 0) {
             tcgen05_fence_after();
-            ring_load(0, a.P + G_W2TS);
-            ring_load(1, a.P + G_W2TS + CHUNK);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 mma3(tmem + T_G2, desc_mn(S_QHI, j), desc_mn(S_QLO, j), desc_mn(S_PHI, j), desc_mn(S_PLO, j), ID_MM144, !first || j > 0);
@@ -459,6 +485,7 @@ __global__ void __launch_bounds__(512, 1) fvp_tc_kernel(const TcFvpArgs a) {
             mma_commit(&bars[0]);
         }
         all_wait_mma();
+        if (tid == 0 && tile + gridDim.x < n_tiles) { ring_load(0, a.P + G_W1S); ring_load(1, a.T + G_W1S); }   // next tile's P1
         // ================= P8: delta1 = (1-h1^2) dh1 -> Q =================
 #pragma unroll 1
         for (int cc = 0; cc < 2; ++cc) {

@@ -59,6 +59,9 @@ void launch_advantages(const double* rew, const float* base, const double* ret, 
 // out[0] = sum(x - shift), out[1] = sum((x - shift)^2) over n doubles (deterministic two-stage)
 void launch_moments(const double* x, long long n, const double* shift_dev, double* scratch, double* out2,
                     cudaStream_t s);
+// device-side finalisation of the statistics (no host round trip between the passes)
+void launch_stats_finalize(const double* mom2, double inv_n, double* stats2, int mode, cudaStream_t s);
+void launch_path_stats(const double* path_ret, int n_paths, double inv_paths_global, double* out4, int pass, cudaStream_t s);
 // white[i] = float((adv[i]-mean)/(std+1e-6)); stats = {mean, std} on device
 void launch_whiten(const double* adv, long long n, const double* stats, float* white, cudaStream_t s);
 // DAPG weights (dapg.py:62-74): rollout w = 1e-2*white/(std(white)+1e-8), demo w = 1e-2*lam

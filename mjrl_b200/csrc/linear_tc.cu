@@ -346,8 +346,8 @@ __global__ void lin_tc_prep_kernel(const float* __restrict__ v, int K0, int A, i
 //
 //   warps 0-15  converters + dy epilogue      warp 16 (one thread)  TMA producer      warp 17 (one thread)  MMA issuer
 //
-//   raw ring slot = 16 consecutive timesteps x K0 floats, one bulk copy per row into a padded pitch (pitch/4 odd: the
-//   8-row x 16-byte phases of the converters' LDS.128 hit distinct banks); 2-4 slots (whatever fits next to the tile).
+//   raw ring slot = 16 consecutive timesteps x K0 floats = one contiguous bulk copy (dense rows; the converters' lane map
+//   keeps their LDS.128 phases on distinct banks); 2-4 slots (whatever fits next to the tile).
 //   staged tile  = as above, but rows are permuted so that the fp16 hi and lo rows of a sample sit in the SAME TMEM lane
 //   quadrant, 8 lanes apart: row(m, t) = 16 (m / 8) + 8 t + m % 8  -> the hi*hi + hi*lo + lo*hi sum is one shuffle,
 //   no shared-memory exchange and no block barrier in the epilogue.
@@ -357,8 +357,8 @@ __global__ void lin_tc_prep_kernel(const float* __restrict__ v, int K0, int A, i
 //   dy (epilogue -> issuer), g2 (GEMM 2 -> converters: the tile buffer may be restaged).
 constexpr int TW_CONV = 16;                       // converter warps
 constexpr int T_THREADS = 32 * (TW_CONV + 2);     // 576
-constexpr int CHUNK_ROWS = 16;                    // rows per ring slot; LM / CHUNK_ROWS = 4 slots' worth per tile
-constexpr int MAX_SLOTS = 4;
+constexpr int CHUNK_ROWS = 16;                    // rows per ring slot; LM / CHUNK_ROWS = 4 slots' worth per tile.  (8-row slots
+constexpr int MAX_SLOTS = 4;                      //  were measured slower: a cp.async.bulk costs its issuer ~250 cycles whatever its size)
 
 struct LinTmaArgs {
     const unsigned char* T; const float* theta;
@@ -369,6 +369,7 @@ struct LinTmaArgs {
     int nfb;           // feature blocks of 128 in use: ceil((K0 + 1) / 128)
     int pitch;         // floats between raw rows in a ring slot
     int slots;         // ring slots
+    int map4x2;        // converter lane map: 0 = a phase reads 8 rows x 1 float4 column, 1 = 4 rows x 2 columns
     int off_v, off_dy, off_f32, off_ring, off_bar;   // shared-memory map (bytes); the staged tile sits at 0
     unsigned long long* prof;                        // developer aid: per-role clock64 sums (nullptr = off), 16 slots
 };
@@ -427,8 +428,8 @@ __global__ void __launch_bounds__(T_THREADS, 1) linear_tc_tma_kernel(const LinTm
 
     if (warp == TW_CONV) {
         // =============================== TMA producer ===============================
-        // lane 0 arms the slot's barrier, then lanes 0..15 each issue ONE row copy of the chunk: a single thread needs
-        // ~135 cycles per cp.async.bulk (measured: 8.7 k cycles per 64-row tile, the bound of the first version)
+        // lane 0 arms the slot's barrier and issues ONE bulk copy for the slot's 16 contiguous rows (the other lanes only
+        // keep the warp converged)
         {
             if (lane == 0) {
                 mbar_expect_tx(&bars[B_V], (uint32_t)v_bytes);
@@ -447,14 +448,16 @@ __global__ void __launch_bounds__(T_THREADS, 1) linear_tc_tma_kernel(const LinTm
                     const long long row0 = tile * LM + (long long)c * CHUNK_ROWS;
                     const int rows = (int)max(0LL, min((long long)CHUNK_ROWS, a.n - row0));
                     if (lane == 0) {
-                        if (rows > 0) mbar_expect_tx(&bars[B_FULL + slot], row_bytes * (uint32_t)rows);
-                        else mbar_arrive(&bars[B_FULL + slot]);        // nothing to load: complete the phase by hand
+                        if (rows > 0) {
+                            mbar_expect_tx(&bars[B_FULL + slot], row_bytes * (uint32_t)rows);
+                            bulk_g2s(smem + a.off_ring + (size_t)slot * chunk_bytes, a.obs + row0 * K0,
+                                     row_bytes * (uint32_t)rows, &bars[B_FULL + slot]);
+                        } else {
+                            mbar_arrive(&bars[B_FULL + slot]);         // nothing to load: complete the phase by hand
+                        }
+                        TMA_PROF(p_issue);
                     }
-                    __syncwarp();                                      // the barrier is armed before any copy can complete
-                    if (lane < rows)
-                        bulk_g2s(smem + a.off_ring + (size_t)slot * chunk_bytes + (size_t)lane * pitch * 4,
-                                 a.obs + (row0 + lane) * K0, row_bytes, &bars[B_FULL + slot]);
-                    if (lane == 0) TMA_PROF(p_issue);
+                    __syncwarp();
                 }
             }
             if (a.prof && lane == 0) { atomicAdd(a.prof + 9, p_wait); atomicAdd(a.prof + 10, p_issue); }
@@ -504,7 +507,10 @@ __global__ void __launch_bounds__(T_THREADS, 1) linear_tc_tma_kernel(const LinTm
         }
     } else {
         // =============================== converters + dy epilogue (warps 0-15) ===============================
-        const int r8 = lane & 7, cidx = lane >> 3;
+        // lane -> (row r8 of the 8-row group, float4 column cidx of the 16-feature block).  Either map gives every
+        // half-warp 8 rows x 2 columns (conflict-free 8-byte stores into one core-matrix row group) ...
+        const int r8 = a.map4x2 ? ((lane & 3) + 4 * ((lane >> 3) & 1)) : (lane & 7);
+        const int cidx = a.map4x2 ? (((lane >> 2) & 1) + 2 * (lane >> 4)) : (lane >> 3);
         const int q = warp & 3, cq = warp >> 2;                      // epilogue: TMEM lane quadrant, 8-action group
         const int e_grp = lane >> 4, e_t = (lane >> 3) & 1;          // epilogue lane -> (sample group, hi/lo row)
         const int e_m = 16 * q + 8 * e_grp + (lane & 7);             // sample of this lane's TMEM row (row = 32 q + lane)
@@ -666,15 +672,18 @@ static bool lin_tma_plan(int K0, int A, bool has_idx, LinTmaArgs* out) {
     LinTmaArgs a;
     a.ap = round_up(A, 8);
     a.nfb = (K0 + 1 + FB - 1) / FB;
-    int pitch = K0;
-    while (((pitch / 4) & 1) == 0) pitch += 4;                        // pitch / 4 odd: conflict-free 8-row LDS.128 phases
-    a.pitch = pitch;
-    const int chunk_bytes = CHUNK_ROWS * pitch * 4;
+    // ONE bulk copy per ring slot: the 16 rows of a slot are contiguous in global memory and land densely (pitch = K0).
+    // (One copy per row into a padded pitch was measured first: the TMA unit needs ~80 cycles per cp.async.bulk whatever
+    //  its size, 5 k cycles per 64-row tile, and the ring ran dry.)  The converters' LDS.128 stays conflict-free by
+    //  choosing which rows x float4-columns the 8 lanes of a phase touch: K0/4 odd -> 8 rows x 1 column, else 4 rows x 2.
+    a.pitch = K0;
+    const int chunk_bytes = CHUNK_ROWS * a.pitch * 4;
     const int v_bytes = 2 * a.ap * LKP * 2, dy_bytes = XR * 2 * a.ap * 2;
     a.off_v = RING * XB_BYTES;
     a.off_dy = a.off_v + v_bytes;
     a.off_f32 = a.off_dy + dy_bytes;
     a.off_ring = round_up(a.off_f32 + SLF_END * 4, 128);
+    a.map4x2 = (((K0 / 4) & 1) == 0) ? 1 : 0;
     const int max_smem = 232448 - 1024;                               // 227 KB opt-in limit minus static shared + slack
     int slots = (max_smem - 256 - a.off_ring) / chunk_bytes;
     if (slots > MAX_SLOTS) slots = MAX_SLOTS;

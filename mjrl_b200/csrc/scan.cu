@@ -222,6 +222,42 @@ void launch_moments(const double* x, long long n, const double* shift_dev, doubl
     moments_stage2<<<1, 256, 0, s>>>(scratch, kMomGrid, out2);
 }
 
+// ---- batch statistics finalised ON the device (mjb_process_paths makes one host round trip, at its end) -----------
+// mode 0: stats[0] = mom[0] * inv_n (mean);  mode 1: stats[1] = sqrt(mom[1] * inv_n) (population std about that mean)
+__global__ void stats_finalize_kernel(const double* __restrict__ mom, double inv_n, double* __restrict__ stats, int mode) {
+    if (mode == 0) stats[0] = mom[0] * inv_n;
+    else stats[1] = sqrt(mom[1] * inv_n);
+}
+void launch_stats_finalize(const double* mom2, double inv_n, double* stats2, int mode, cudaStream_t s) {
+    stats_finalize_kernel<<<1, 1, 0, s>>>(mom2, inv_n, stats2, mode);
+}
+// pass 0: out[0] = sum, out[1] = -min, out[2] = max of the per-path returns (local paths);
+// pass 1: out[3] = sum (r - mean)^2 with mean = out[0] * inv_paths_global (out[0] all-reduced in between)
+__global__ void path_stats_kernel(const double* __restrict__ pr, int n_paths, double inv_paths_global, double* __restrict__ out,
+                                  int pass) {
+    __shared__ double red[32];
+    __shared__ double redm[64];
+    const double mean = pass ? out[0] * inv_paths_global : 0.0;
+    double s = 0.0, mn = INFINITY, mx = -INFINITY;
+    for (int i = threadIdx.x; i < n_paths; i += blockDim.x) {
+        const double v = pr[i];
+        if (pass) { s += (v - mean) * (v - mean); }
+        else { s += v; mn = fmin(mn, v); mx = fmax(mx, v); }
+    }
+    s = block_sum(s, red);
+    if (pass) { if (threadIdx.x == 0) out[3] = s; return; }
+    for (int d = 16; d > 0; d >>= 1) { mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, d)); mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d)); }
+    if ((threadIdx.x & 31) == 0) { redm[threadIdx.x >> 5] = mn; redm[32 + (threadIdx.x >> 5)] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { mn = fmin(mn, redm[w]); mx = fmax(mx, redm[32 + w]); }
+        out[0] = s; out[1] = -mn; out[2] = mx;
+    }
+}
+void launch_path_stats(const double* path_ret, int n_paths, double inv_paths_global, double* out4, int pass, cudaStream_t s) {
+    path_stats_kernel<<<1, 256, 0, s>>>(path_ret, n_paths, inv_paths_global, out4, pass);
+}
+
 __global__ void whiten_kernel(const double* __restrict__ adv, long long n, const double* __restrict__ stats,
                               float* __restrict__ white) {
     const double mean = stats[0], denom = stats[1] + 1e-6;

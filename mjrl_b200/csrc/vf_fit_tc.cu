@@ -140,7 +140,9 @@ __device__ __forceinline__ void gemm3(uint32_t d, uint32_t ah, uint32_t al, uint
                                       uint32_t bh, uint32_t bl, uint32_t b_step, uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc) {
     uint64_t dah = make_desc(ah, a_lbo, a_sbo), dal = make_desc(al, a_lbo, a_sbo);
     uint64_t dbh = make_desc(bh, b_lbo, b_sbo), dbl = make_desc(bl, b_lbo, b_sbo);
-#pragma unroll
+    // NOT unrolled: only one thread runs this and the tensor queue paces it, while every unrolled MMA costs ~10
+    // instructions of a loop body that has to stay inside the 32 KB instruction cache (see the note at the kernel)
+#pragma unroll 1
     for (int j = 0; j < KS; ++j) {
         mma_f16(d, dah, dbh, idesc, j > 0);
         mma_f16(d, dal, dbh, idesc, true);
@@ -159,7 +161,7 @@ __device__ __forceinline__ void gemm2c(uint32_t d, uint32_t ah, uint32_t al, uin
                                        uint32_t idesc_2n, uint32_t idesc_n) {
     uint64_t dah = make_desc(ah, a_lbo, a_sbo), dal = make_desc(al, a_lbo, a_sbo);
     uint64_t dbh = make_desc(bh, b_lbo, b_sbo);
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < KS; ++j) {
         mma_f16(d, dah, dbh, idesc_2n, j > 0);
         mma_f16(d, dal, dbh, idesc_n, true);
@@ -168,6 +170,11 @@ __device__ __forceinline__ void gemm2c(uint32_t d, uint32_t ah, uint32_t al, uin
     }
 }
 
+// PROF = true instantiates the per-phase clock64 counters (tools/vf_fit_profile.py); the production instance carries none
+// of that code.  Code size matters here: a single resident CTA runs a ~2.7 k-instruction step body 15 624 times, and a
+// body that does not fit the 32 KB instruction cache is re-fetched from L2 every step (the fetch stalls showed up as
+// ~1.3 k unexplained cycles per step that moved with whatever code ran "cold").
+template <bool PROF>
 __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     float* sf = reinterpret_cast<float*>(smem + S_F32);
@@ -281,7 +288,7 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
     auto sync_ops = [&]() { fence_proxy_async(); tcgen05_fence_before(); __syncthreads(); };
 
     long long t_last = clock64();
-#define TC_PROF(i) do { if (a.prof && tid == 0) { const long long _t = clock64(); s_prof[i] += _t - t_last; t_last = _t; } } while (0)
+#define TC_PROF(i) do { if (PROF && tid == 0) { const long long _t = clock64(); s_prof[i] += _t - t_last; t_last = _t; } } while (0)
 
     AdamP ap;
     ap.one_m_b1 = 1.0f - a.beta1; ap.b2 = a.beta2; ap.one_m_b2 = 1.0f - a.beta2; ap.eps = a.eps; ap.reg = a.reg;
@@ -302,11 +309,7 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
             mma_commit(&bars[0]);
         }
         TC_PROF(14);                                                 // (issue of the six layer-1 MMAs)
-        if (s + 1 < a.steps) load_rows(i1);                          // rows of step s+1: a whole step to land
-        i1 = i2;
-        if (s + 3 < a.steps) i2 = a.perm[(size_t)(s + 3) * NB + gn];
         const float4 cst = cst_next;
-        if (s + 1 < a.steps) cst_next = a.consts[s + 1];
         ap.rbc2_sqrt = cst.x; ap.neg_step = cst.y;
         ap2.rbc2_sqrt = pk2(cst.x, cst.x); ap2.neg_step = pk2(cst.y, cst.y);
         TC_PROF(0);
@@ -341,6 +344,12 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
             mma_commit(&bars[0]);
         }
         TC_PROF(3);
+        // gathers for the coming steps, issued while the layer-2 GEMM runs and nobody has work: rows of step s+1 (consumed
+        // by stage_x in the gW2 shadow below), the permutation entry of step s+3, the Adam constants of step s+1
+        if (s + 1 < a.steps) load_rows(i1);
+        i1 = i2;
+        if (s + 3 < a.steps) i2 = a.perm[(size_t)(s + 3) * NB + gn];
+        if (s + 1 < a.steps) cst_next = a.consts[s + 1];
         wait0();
         TC_PROF(4);
         float h2[16];
@@ -538,7 +547,7 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
         TC_PROF(12);
     }
     __syncthreads();
-    if (a.prof && tid < 16) a.prof[tid] += s_prof[tid];
+    if (PROF && a.prof && tid < 16) a.prof[tid] += s_prof[tid];
 
     // ---- write the state back (natural layout) ----
     {
@@ -630,9 +639,10 @@ cudaError_t launch_vf_fit_tc(const VfFitArgs& v, const float* feat, const float*
     a.K = v.K; a.steps = v.steps; a.feat = feat; a.ret32 = ret32; a.perm = v.perm;
     a.reg = v.reg; a.beta1 = v.beta1; a.beta2 = v.beta2; a.eps = v.eps;
     a.w = v.w; a.m = v.m; a.v = v.v; a.consts = consts; a.prof = g_tc_prof;
-    cudaError_t e = cudaFuncSetAttribute(vf_fit_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S_TOTAL);
+    auto kern = a.prof ? vf_fit_tc_kernel<true> : vf_fit_tc_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S_TOTAL);
     if (e != cudaSuccess) return e;
-    vf_fit_tc_kernel<<<1, NT, S_TOTAL, s>>>(a);
+    kern<<<1, NT, S_TOTAL, s>>>(a);
     return cudaGetLastError();
 }
 
