@@ -452,6 +452,7 @@ def run_gpu(args, cfg, rank, world, local_rank):
     # ---------------- FVP/s: device-resident CG (10 x {FVP + all-reduce + fused update}) ----------------
     g = eng.vpg() if cfg["algo"] != "dapg" else eng.vpg(True, 1.0)
     eng.cg(g, iters=CG_ITERS, damping=DAMPING)
+    eng.lib.mjb_policy_cg(eng.h, None, CG_ITERS, DAMPING, 0.0, None, 0, None)    # warm-up of exactly the timed call (graph capture)
     barrier()
     reps = 5
     eng.event_record(2)

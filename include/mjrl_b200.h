@@ -86,6 +86,13 @@ int  mjb_batch_upload(mjb_engine* e, int which, int32_t n_paths, const double* c
 /* Same, from already-concatenated host-or-device arrays (fp64 host layout of np.concatenate). */
 int  mjb_batch_upload_flat(mjb_engine* e, int which, int32_t n_paths, const double* obs, const double* act,
                            const double* rew, const int32_t* len, const uint8_t* terminated);
+/* Rollouts that already live on the device as batched arrays obs [n_traj][horizon][obs_dim], act [..][act_dim], rew
+ * [n_traj][horizon] (float32, or float64 when is_f64) -- what the learned-model rollouts of
+ * algos/model_accel/sampling.py:16-90 produce and algos/model_accel/model_accel_npg.py:107-127 would otherwise slice
+ * into host path dicts.  len[i] <= horizon (NULL = all full) keeps a prefix of trajectory i (termination / truncation,
+ * model_accel_npg.py:129-158).  Packed device-to-device into the rollout batch; no host copy of the samples. */
+int  mjb_batch_upload_rollouts(mjb_engine* e, int32_t n_traj, int32_t horizon, const void* obs, const void* act,
+                               const void* rew, int is_f64, const int32_t* len, const uint8_t* terminated);
 /* Advantages computed elsewhere (callers of train_from_paths that bring path["advantages"]). */
 int  mjb_batch_set_advantages(mjb_engine* e, const double* adv_concat);
 /* Already-whitened advantages as the reference's CPI_surrogate / flat_vpg take them (fp32 after .float(),

@@ -51,6 +51,7 @@ _SIGNATURES = {
     "mjb_comm_init": (C.c_int, [_P, _P]),
     "mjb_batch_upload": (C.c_int, [_P, C.c_int, C.c_int32, _P, _P, _P, _P, _P]),
     "mjb_batch_upload_flat": (C.c_int, [_P, C.c_int, C.c_int32, _P, _P, _P, _P, _P]),
+    "mjb_batch_upload_rollouts": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, C.c_int, _P, _P]),
     "mjb_batch_set_advantages": (C.c_int, [_P, _P]),
     "mjb_batch_set_baseline": (C.c_int, [_P, _P]),
     "mjb_batch_set_returns": (C.c_int, [_P, _P]),

@@ -185,14 +185,72 @@ class BatchREINFORCE:
             self.logger.log_kv('VF_error_after', error_after)
         return eval_statistics
 
+    def update_from_rollouts(self, rollouts, gamma=0.995, gae_lambda=0.97, lengths=None, terminated=None):
+        """The post-rollout update on DEVICE-RESIDENT batched rollouts -- the hand-off the model-based caller wants
+        (algos/model_accel/model_accel_npg.py:107-181: learned-model rollouts are already batched tensors
+        `rollouts['observations'|'actions'|'rewards']` of shape [n_traj, horizon, ...], model_accel/sampling.py:16-90;
+        the reference slices them into host path dicts and concatenates them again).  Here they are packed on the device
+        (`mjb_batch_upload_rollouts`) and the whole step -- returns, GAE, whitening, VPG, CG, step, baseline fit -- runs
+        without the samples ever visiting the host.  `lengths[i] <= horizon` keeps a prefix of trajectory i (termination
+        function / ensemble truncation, :129-158), `terminated[i]` marks it as terminated for the GAE bootstrap.
+        numpy arrays / CPU tensors are accepted and moved with torch.  Returns the reference's base_stats list."""
+        import torch
+        if not hasattr(self.baseline, "fit_begin_resident"):
+            raise NotImplementedError("update_from_rollouts needs the device MLPBaseline (host baselines want path dicts)")
+        if getattr(self, "input_normalization", None):
+            raise NotImplementedError("input_normalization reads host observations: use update_from_paths")
+        dev = torch.device("cuda", runtime.device_ordinal())
+        tens = []
+        for k in ("observations", "actions", "rewards"):
+            x = rollouts[k]
+            x = x if torch.is_tensor(x) else torch.as_tensor(np.asarray(x))
+            tens.append(x.to(dev) if not x.is_cuda else x)
+        dt = torch.float64 if any(t.dtype == torch.float64 for t in tens) else torch.float32
+        obs, act, rew = (t.to(dt) for t in tens)
+        n_traj, H = int(obs.shape[0]), int(obs.shape[1])
+        n = int(np.sum(lengths)) if lengths is not None else n_traj * H
+        eng = self._eng(n + self._demo_samples(), n_traj)
+        eng.session_paths = None
+        eng.upload_rollouts(obs, act, rew, lengths, terminated)
+        self._push_policy(eng)
+        eng.compute_returns(gamma)
+        error_before = self.baseline.fit_begin_resident(eng, return_errors=self.save_logs)
+        fit_started = True
+        try:
+            eng.vf_predict(prefit=True)                      # pre-fit baseline, as in the reference's program order
+            eng.compute_advantages(gamma, gae_lambda)
+            stats = self._train_resident(eng, None)
+        except BaseException:
+            if fit_started:
+                try:
+                    self.baseline.fit_end(return_errors=False)
+                except Exception:
+                    pass
+            raise
+        if self.save_logs:
+            self.logger.log_kv('num_samples', n)
+            ts = timer.time()
+            error_after = self.baseline.fit_end(return_errors=True)
+            self.logger.log_kv('time_VF', timer.time() - ts)
+            self.logger.log_kv('VF_error_before', error_before)
+            self.logger.log_kv('VF_error_after', error_after)
+        else:
+            self.baseline.fit_defer()
+        return stats
+
     # ------------------------------------------------------------------ shared pieces of train_from_paths
     def process_paths(self, paths):
         """batch_reinforce.py:178-197: whitening + return statistics on the device; returns the reference's tuple
-        except that the concatenated arrays stay on the GPU (None placeholders)."""
-        eng = self._resident(paths)
-        if "advantages" in paths[0] and not eng.adv_on_device:
-            # anything but advantages the engine itself just computed for this very upload comes from the path dicts
-            eng.set_advantages(np.concatenate([p["advantages"] for p in paths]))
+        except that the concatenated arrays stay on the GPU (None placeholders).  paths=None: the engine's resident
+        batch with device-computed advantages (update_from_rollouts)."""
+        if paths is None:
+            eng = self._engine
+            assert eng is not None and eng.adv_on_device
+        else:
+            eng = self._resident(paths)
+            if "advantages" in paths[0] and not eng.adv_on_device:
+                # anything but advantages the engine itself just computed for this very upload comes from the path dicts
+                eng.set_advantages(np.concatenate([p["advantages"] for p in paths]))
         st = eng.process_paths()
         base_stats = [st.mean_return, st.std_return, st.min_return, st.max_return]
         running = st.mean_return if self.running_score is None else 0.9 * self.running_score + 0.1 * st.mean_return
@@ -234,4 +292,5 @@ class BatchREINFORCE:
             self.logger.log_kv('kl_dist', st.kl_dist)
             self.logger.log_kv('surr_improvement', st.surr_after - st.surr_before)
             self.logger.log_kv('running_score', self.running_score)
-            self._log_success(paths)
+            if paths is not None:
+                self._log_success(paths)

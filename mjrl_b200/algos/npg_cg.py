@@ -88,6 +88,10 @@ class NPG(BatchREINFORCE):
         return 0.0
 
     def train_from_paths(self, paths):
+        return self._train_resident(None, paths)
+
+    def _train_resident(self, eng, paths):
+        """train_from_paths on host path dicts, or (paths=None) on the engine's resident device batch."""
         t0 = timer.time()
         _, _, _, base_stats, self.running_score = self.process_paths(paths)
         eng = self._engine

@@ -199,6 +199,16 @@ class MLPBaseline:
         perms = np.stack([runtime.global_permutation(n_glob) for _ in range(self.epochs)])
         return eng.vf_fit_begin(perms, self.batch_size, self.learn_rate, self.reg_coef, return_errors=return_errors)
 
+    def fit_begin_resident(self, eng, return_errors=False):
+        """fit_begin for a batch that is already the engine's resident rollout batch with its returns computed on the
+        device (BatchREINFORCE.update_from_rollouts): no path dicts, no upload."""
+        self._bind(eng)
+        self._eng()
+        assert eng.have_returns, "compute the returns on the engine first"
+        n_glob = eng.n_global()
+        perms = np.stack([runtime.global_permutation(n_glob) for _ in range(self.epochs)])
+        return eng.vf_fit_begin(perms, self.batch_size, self.learn_rate, self.reg_coef, return_errors=return_errors)
+
     def fit_end(self, return_errors=False):
         self._fit_pending = False
         err = self._engine.vf_fit_end(return_errors)

@@ -758,6 +758,33 @@ int mjb_batch_upload(mjb_engine* e, int which, int32_t n_paths, const double* co
     return finish_upload(e, which, n_paths, len, terminated, n);
 }
 
+int mjb_batch_upload_rollouts(mjb_engine* e, int32_t n_traj, int32_t horizon, const void* obs, const void* act, const void* rew,
+                              int is_f64, const int32_t* len, const uint8_t* terminated) {
+    if (n_traj < 0 || n_traj > e->cfg.max_paths) FAIL(e, "too many paths for max_paths");
+    if (horizon < 1) FAIL(e, "bad horizon");
+    if (e->fit_in_flight && e->fit_reads_batch && mjb_vf_fit_end(e, nullptr)) return -1;
+    if (is_host_ptr(obs) || is_host_ptr(act) || is_host_ptr(rew))
+        FAIL(e, "mjb_batch_upload_rollouts takes DEVICE arrays (host trajectories go through mjb_batch_upload)");
+    long long n = 0;
+    std::vector<int32_t> lens((size_t)n_traj, horizon);
+    for (int i = 0; i < n_traj; ++i) {
+        if (len) { if (len[i] < 0 || len[i] > horizon) FAIL(e, "path length outside [0, horizon]"); lens[i] = len[i]; }
+        n += lens[i];
+    }
+    if (n > e->cap) FAIL(e, "batch exceeds max_samples");
+    CK(e, cudaSetDevice(e->cfg.device));
+    // path offsets first (the pack kernels read them), then three device-to-device packs: nothing crosses PCIe
+    e->h_path_off.assign((size_t)n_traj + 1, 0);
+    for (int i = 0; i < n_traj; ++i) e->h_path_off[i + 1] = e->h_path_off[i] + lens[i];
+    CK(e, cudaMemcpyAsync(e->path_off, e->h_path_off.data(), sizeof(int) * (n_traj + 1), cudaMemcpyHostToDevice, e->stream));
+    launch_pack_rollouts(obs, is_f64, horizon, e->cfg.obs_dim, e->path_off, n_traj, e->obs, 0, e->stream);
+    launch_pack_rollouts(act, is_f64, horizon, e->cfg.act_dim, e->path_off, n_traj, e->act, 0, e->stream);
+    launch_pack_rollouts(rew, is_f64, horizon, 1, e->path_off, n_traj, e->rew, 1, e->stream);
+    e->launches += 3;
+    CK(e, cudaGetLastError());
+    return finish_upload(e, MJB_BATCH_ROLLOUT, n_traj, lens.data(), terminated, n);
+}
+
 int mjb_batch_upload_flat(mjb_engine* e, int which, int32_t n_paths, const double* obs, const double* act,
                           const double* rew, const int32_t* len, const uint8_t* terminated) {
     if (which != MJB_BATCH_ROLLOUT && which != MJB_BATCH_DEMO) FAIL(e, "bad batch id");

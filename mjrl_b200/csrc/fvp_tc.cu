@@ -107,6 +107,21 @@ __device__ __forceinline__ void store_split16(unsigned char* smem, int off_hi, i
     }
 }
 
+// 8 consecutive columns [c0, c0+8) of row m -> one 16-byte core-matrix row of the hi buffer and one of the lo buffer
+__device__ __forceinline__ void store_split8(unsigned char* smem, int off_hi, int off_lo, int m, int c0, const float (&v)[8]) {
+    __half2 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float a = v[2 * j], b = v[2 * j + 1];
+        h[j] = __floats2half2_rn(a, b);                           // one cvt.rn.f16x2.f32 for two values
+        const float2 back = __half22float2(h[j]);
+        l[j] = __floats2half2_rn(a - back.x, b - back.y);
+    }
+    const int o = (c0 >> 3) * LBY + (m >> 3) * 128 + (m & 7) * 16;
+    *reinterpret_cast<uint4*>(smem + off_hi + o) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(smem + off_lo + o) = *reinterpret_cast<const uint4*>(l);
+}
+
 // D (+)= A * B^T with two-term fp16 operands: hi*hi + lo*hi + hi*lo
 __device__ __forceinline__ void mma3(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, uint32_t idesc, bool acc) {
     mma_f16(d, a_hi, b_hi, idesc, acc);
@@ -248,33 +263,27 @@ __global__ void __launch_bounds__(512, 1) fvp_tc_kernel(const TcFvpArgs a) {
     };
     float gb3_acc = 0.0f;                                             // thread a < 8: running sum_m dy[m][a]
     const long long n_tiles = (a.n + TM - 1) / TM;
-    // Input staging: a 128 x obs_dim tile is <= 31 x 128 elements = at most 8 per thread.  The (row, feature) of each
-    // slot never changes, so it is decoded once; the raw values of the NEXT tile are fetched into registers while the
-    // current tile computes (their L2 / HBM latency used to sit in front of every tile).
-    constexpr int XS = 8;
-    const int n_el = TM * a.obs_dim;
-    uint32_t x_rk[XS];                                                // row | feature << 8 ; 0xffffffff = unused slot
-    float x_raw[XS];
+    // Input staging: thread -> (row = tid / 4, 8 consecutive features (tid % 4) * 8 ..), i.e. one 16-byte core-matrix row
+    // of the staged tile per thread (one vector store for the hi half, one for the lo half); four threads read a row's
+    // <= 124 contiguous bytes.  The raw values of the NEXT tile are fetched into registers while the current tile
+    // computes (their L2 / HBM latency used to sit in front of every tile).  The ones column (bias gradient through
+    // G1) sits at feature obs_dim.
+    const int x_r = tid >> 2, x_k0 = (tid & 3) * 8;
+    float x_raw[8], x_sh[8], x_ri[8];
 #pragma unroll
-    for (int i = 0; i < XS; ++i) {
-        const int f = tid + 512 * i;
-        x_rk[i] = f < n_el ? (uint32_t)(f / a.obs_dim) | ((uint32_t)(f % a.obs_dim) << 8) : 0xffffffffu;
-        x_raw[i] = 0.0f;
+    for (int j = 0; j < 8; ++j) {
+        const int k = x_k0 + j;
+        x_raw[j] = 0.0f;
+        x_sh[j] = k < a.obs_dim ? a.in_shift[k] : 0.0f;
+        x_ri[j] = k < a.obs_dim ? 1.0f / (a.in_scale[k] + 1e-8f) : 0.0f;
     }
     auto fetch_tile = [&](long long tile) {
-        const long long base = tile * TM;
+        const long long row = tile * TM + x_r;
+        const bool rv = row < a.n;
+        const long long rr = rv ? (a.idx ? (long long)a.idx[row] : row) : 0;
+        const float* src = a.obs + rr * a.obs_dim + x_k0;
 #pragma unroll
-        for (int i = 0; i < XS; ++i) {
-            x_raw[i] = 0.0f;
-            if (x_rk[i] != 0xffffffffu) {
-                const int r = x_rk[i] & 0xff, k = x_rk[i] >> 8;
-                const long long row = base + r;
-                if (row < a.n) {
-                    const long long rr = a.idx ? (long long)a.idx[row] : row;
-                    x_raw[i] = __ldg(a.obs + rr * a.obs_dim + k);
-                }
-            }
-        }
+        for (int j = 0; j < 8; ++j) x_raw[j] = (rv && x_k0 + j < a.obs_dim) ? __ldg(src + j) : 0.0f;
     };
     if ((long long)blockIdx.x < n_tiles) fetch_tile(blockIdx.x);
     long long it = 0;
@@ -282,20 +291,17 @@ __global__ void __launch_bounds__(512, 1) fvp_tc_kernel(const TcFvpArgs a) {
         const long long base = tile * TM;
         const bool first = (it % FLUSH_TILES == 0);                  // first tile of an accumulation group
         // ================= P0: stage the input tile (transform, split) =================
+        {
+            float xv[8];
+            const bool rv = base + x_r < a.n;
 #pragma unroll
-        for (int i = 0; i < XS; ++i) {
-            if (x_rk[i] != 0xffffffffu) {
-                const int r = x_rk[i] & 0xff, k = x_rk[i] >> 8;
-                const float v = (base + r < a.n) ? (x_raw[i] - a.in_shift[k]) / (a.in_scale[k] + 1e-8f) : 0.0f;
-                __half h, l;
-                split16(v, h, l);
-                const uint32_t o = core_offset(r, k, 128);
-                *reinterpret_cast<__half*>(smem + S_XHI + o) = h;
-                *reinterpret_cast<__half*>(smem + S_XLO + o) = l;
+            for (int j = 0; j < 8; ++j) {
+                xv[j] = rv ? (x_raw[j] - x_sh[j]) * x_ri[j] : 0.0f;
+                if (x_k0 + j == a.obs_dim) xv[j] = 1.0f;
             }
+            store_split8(smem, S_XHI, S_XLO, x_r, x_k0, xv);
         }
         if (tile + gridDim.x < n_tiles) fetch_tile(tile + gridDim.x);     // next tile: in flight under this tile's phases
-        if (it == 0 && tid < 128) *reinterpret_cast<__half*>(smem + S_XHI + core_offset(tid, a.obs_dim, 128)) = __float2half_rn(1.0f);
         fence_proxy_async();
         tcgen05_fence_before();
         __syncthreads();

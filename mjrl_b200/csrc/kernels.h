@@ -51,6 +51,9 @@ cudaError_t launch_linear(int mode, const LinArgs& args, int grid, cudaStream_t 
 // ---- scan.cu : returns / GAE / whitening / packing helpers
 void launch_f64_to_f32(const double* src, float* dst, long long n, cudaStream_t s);
 void launch_tstep(const int* path_off, int n_paths, int* tstep, cudaStream_t s);
+// device [n_traj][H][width] (float32 or float64) -> packed valid prefixes (float32 or float64) at row offsets path_off
+void launch_pack_rollouts(const void* src, int is_f64, int H, int width, const int* path_off, int n_traj, void* dst, int dst_f64,
+                          cudaStream_t s);
 void launch_returns(const double* rew, const int* path_off, int n_paths, double gamma, double* ret, cudaStream_t s);
 void launch_path_sums(const double* rew, const int* path_off, int n_paths, double* path_ret, cudaStream_t s);
 void launch_advantages(const double* rew, const float* base, const double* ret, const int* path_off,

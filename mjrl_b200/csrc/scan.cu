@@ -21,6 +21,28 @@ void launch_f64_to_f32(const double* src, float* dst, long long n, cudaStream_t 
     f64_to_f32_kernel<<<grid, 256, 0, s>>>(src, dst, n);
 }
 
+// Device-resident rollouts [n_traj][H][width] (model-based rollouts, model_accel/sampling.py:16-90) -> packed rows of the
+// valid prefixes in path order: trajectory i contributes len[i] rows at row offset path_off[i].  One CTA per trajectory.
+template <typename T, typename D>
+__global__ void pack_rollouts_kernel(const T* __restrict__ src, int H, int width, const int* __restrict__ path_off, int n_traj,
+                                     D* __restrict__ dst) {
+    for (int p = blockIdx.x; p < n_traj; p += gridDim.x) {
+        const long long o = path_off[p], n = (long long)(path_off[p + 1] - path_off[p]) * width;
+        const T* s = src + (size_t)p * H * width;
+        D* d = dst + o * width;
+        for (long long i = threadIdx.x; i < n; i += blockDim.x) d[i] = (D)s[i];
+    }
+}
+void launch_pack_rollouts(const void* src, int is_f64, int H, int width, const int* path_off, int n_traj, void* dst, int dst_f64,
+                          cudaStream_t s) {
+    if (n_traj <= 0) return;
+    const int grid = min(n_traj, 148 * 8);
+    if (is_f64 && dst_f64) pack_rollouts_kernel<double, double><<<grid, 256, 0, s>>>((const double*)src, H, width, path_off, n_traj, (double*)dst);
+    else if (is_f64) pack_rollouts_kernel<double, float><<<grid, 256, 0, s>>>((const double*)src, H, width, path_off, n_traj, (float*)dst);
+    else if (dst_f64) pack_rollouts_kernel<float, double><<<grid, 256, 0, s>>>((const float*)src, H, width, path_off, n_traj, (double*)dst);
+    else pack_rollouts_kernel<float, float><<<grid, 256, 0, s>>>((const float*)src, H, width, path_off, n_traj, (float*)dst);
+}
+
 __global__ void tstep_kernel(const int* __restrict__ path_off, int n_paths, int* __restrict__ tstep) {
     for (int p = blockIdx.x; p < n_paths; p += gridDim.x) {
         const int o = path_off[p], T = path_off[p + 1] - o;

@@ -137,6 +137,25 @@ class Engine:
         self._uploaded(which, lens)
         return self.n
 
+    def upload_rollouts(self, obs, act, rew, lens=None, terminated=None):
+        """Device-resident batched rollouts: torch CUDA tensors obs [n, H, obs_dim], act [n, H, act_dim], rew [n, H]
+        (float32 or float64, all the same dtype).  lens (optional, <= H per trajectory) keeps prefixes."""
+        import torch
+        assert obs.is_cuda and act.is_cuda and rew.is_cuda, "upload_rollouts takes CUDA tensors"
+        assert obs.dtype == act.dtype == rew.dtype and obs.dtype in (torch.float32, torch.float64)
+        obs, act, rew = obs.contiguous(), act.contiguous(), rew.contiguous()
+        n_traj, H = int(obs.shape[0]), int(obs.shape[1])
+        assert obs.shape[2] == self.obs_dim and act.shape[2] == self.act_dim and tuple(rew.shape) == (n_traj, H)
+        lens_a = np.full(n_traj, H, np.int32) if lens is None else np.ascontiguousarray(lens, dtype=np.int32)
+        term = np.zeros(n_traj, np.uint8) if terminated is None else np.ascontiguousarray(terminated, dtype=np.uint8)
+        torch.cuda.current_stream(obs.device).synchronize()       # the producers of the tensors are done
+        self._ck(self.lib.mjb_batch_upload_rollouts(self.h, n_traj, H, C.c_void_p(obs.data_ptr()), C.c_void_p(act.data_ptr()),
+                                                    C.c_void_p(rew.data_ptr()), int(obs.dtype == torch.float64), _ptr(lens_a),
+                                                    _ptr(term)), "batch_upload_rollouts")
+        self.synchronize()                                        # the tensors may be freed / reused by the caller now
+        self._uploaded(ROLLOUT, lens_a)
+        return self.n
+
     def set_advantages(self, adv_concat):
         a = np.ascontiguousarray(adv_concat, dtype=np.float64)
         assert a.shape[0] == self.n

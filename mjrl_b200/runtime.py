@@ -21,11 +21,17 @@ def _dist():
     return 1, 0
 
 
+def device_ordinal():
+    """CUDA ordinal of this process' engine (LOCAL_RANK under torchrun, MJRL_B200_DEVICE otherwise)."""
+    world, _ = _dist()
+    return int(os.environ.get("LOCAL_RANK", "0")) if world > 1 else int(os.environ.get("MJRL_B200_DEVICE", "0"))
+
+
 def get_engine(obs_dim, act_dim, hidden=None, vf_hidden=(128, 128), min_log_std=-3.0, need_samples=0, need_paths=0):
     """Return (creating or growing as needed) the engine for this shape.  hidden=None matches any policy
     shape with the same obs/act dims (used by stand-alone baselines / process_samples calls)."""
     world, rank = _dist()
-    device = int(os.environ.get("LOCAL_RANK", "0")) if world > 1 else int(os.environ.get("MJRL_B200_DEVICE", "0"))
+    device = device_ordinal()
     key = None
     if hidden is None:
         for k in _engines:

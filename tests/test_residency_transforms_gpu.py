@@ -239,3 +239,56 @@ def test_deferred_fit_is_joined_by_readers(cuda_device):
         a.update_from_paths(golden_paths(g), m["gamma"], m["lam"])
     assert np.array_equal(bl.get_flat_weights(), bl2.get_flat_weights())
     assert np.array_equal(pol.get_param_values(), pol2.get_param_values())
+
+
+def test_update_from_rollouts_equals_update_from_paths(cuda_device):
+    """Device-resident batched rollouts [n_traj, H, dim] (the learned-model hand-off of model_accel_npg.py:107-181) with
+    per-trajectory prefix lengths and termination flags: same parameters, baseline weights and statistics -- bit for
+    bit -- as the same trajectories arriving as host path dicts."""
+    import torch
+    from mjrl_b200.algos.trpo import TRPO
+    from mjrl_b200.baselines.mlp_baseline import MLPBaseline
+    from mjrl_b200.policies.gaussian_mlp import MLP
+    from mjrl_b200.utils.gym_env import EnvSpec
+    rng = np.random.RandomState(3)
+    n_traj, H, od, ad = 37, 160, 17, 6
+    obs, act, rew = rng.randn(n_traj, H, od), rng.randn(n_traj, H, ad), rng.randn(n_traj, H)
+    lens = rng.randint(5, H + 1, size=n_traj).astype(np.int32)
+    lens[:5] = H
+    term = (lens < H).astype(np.uint8)
+    es = EnvSpec(od, ad, H)
+
+    def agent():
+        pol = MLP(es, hidden_sizes=(128, 128), seed=11)
+        torch.manual_seed(5)
+        bl = MLPBaseline(es, reg_coef=1e-3, batch_size=64, epochs=1, learn_rate=1e-3)
+        a = TRPO(None, pol, bl, kl_dist=0.01)
+        a.verbose = False
+        return a, pol, bl
+
+    a1, p1, b1 = agent()
+    paths = [dict(observations=obs[i, :lens[i]].copy(), actions=act[i, :lens[i]].copy(), rewards=rew[i, :lens[i]].copy(),
+                  terminated=bool(term[i])) for i in range(n_traj)]
+    np.random.seed(9)
+    s1 = a1.update_from_paths(paths, 0.995, 0.97)
+    w1 = b1.get_flat_weights()
+    a2, p2, b2 = agent()
+    dev = torch.device("cuda:0")
+    roll = dict(observations=torch.from_numpy(obs).to(dev), actions=torch.from_numpy(act).to(dev), rewards=torch.from_numpy(rew).to(dev))
+    h2d0 = None
+    np.random.seed(9)
+    eng_before = a2._eng(int(lens.sum()), n_traj)
+    h2d0 = eng_before.transfer_stats()[0]
+    s2 = a2.update_from_rollouts(roll, 0.995, 0.97, lengths=lens, terminated=term)
+    moved = a2._engine.transfer_stats()[0] - h2d0
+    assert moved < 2 * 1024 * 1024, moved                    # parameters / permutation only: the samples never cross PCIe
+    assert np.array_equal(p1.get_param_values(), p2.get_param_values())
+    assert np.array_equal(w1, b2.get_flat_weights())
+    np.testing.assert_allclose(s1, s2, rtol=1e-12)
+    assert a1.last_step.backtracks == a2.last_step.backtracks
+    # float32 device tensors take the same path (rounded where the host staging would round)
+    a3, p3, b3 = agent()
+    np.random.seed(9)
+    a3.update_from_rollouts({k: v.float() for k, v in roll.items()}, 0.995, 0.97, lengths=lens, terminated=term)
+    th0 = MLP(es, hidden_sizes=(128, 128), seed=11).get_param_values()
+    assert one_minus_cos(p3.get_param_values() - th0, p1.get_param_values() - th0) < 1e-4
