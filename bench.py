@@ -580,9 +580,19 @@ def run_gpu(args, cfg, rank, world, local_rank):
             "fit_us_per_adam_step": fit_us, "fit_adam_steps": fit_steps,
             "roofline": roof, "roofline_hbm": hbm, "cpu_baseline": cpu, "trpo_backtrack_check": bt_check}
     print(json.dumps(line), flush=True)
+    _exit_watchdog(60)
     runtime.shutdown()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def _exit_watchdog(seconds):
+    """The result line is out; a teardown that does not finish (a peer rank died, a communicator that will not drain)
+    must not keep the launcher waiting: end the process after `seconds`."""
+    import threading
+    t = threading.Timer(seconds, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
 
 
 def main():

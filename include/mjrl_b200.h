@@ -209,7 +209,7 @@ int  mjb_vf_fit_timing(mjb_engine* e, float* last_ms);
 /* ---- developer aids (used by tools/, not by the Python mirror) ---------------------------------- */
 /* per-phase clock64 counters of the tensor-core fit kernel / of the linear-policy FVP kernel: enable = 1 arms the
  * counters, enable = 0 reads them back (16 values each) and disarms. */
-int  mjb_dev_vf_profile(mjb_engine* e, long long* out16, int enable);
+int  mjb_dev_vf_profile(mjb_engine* e, long long* out16, int enable);   /* enable: 1 arm, 0 read head CTA + disarm, 2 read K-split helper 0 */
 int  mjb_dev_lin_profile(mjb_engine* e, long long* out8, int enable);
 
 #ifdef __cplusplus

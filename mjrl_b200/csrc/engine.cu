@@ -114,6 +114,7 @@ struct mjb_engine {
     int vf_tc_on = 1;         // fit kernel: 1 = single-SM tensor-core kernel where the shape allows, 0 = single-CTA FMA kernel
     int vf_sms = 1;           // SMs the fit kernel in flight occupies
     float4* vf_consts = nullptr; int vf_consts_cap = 0;   // per-step Adam constants of the fit kernels
+    void* vf_ks = nullptr;    // hand-off scratch of the K-split tensor-core fit (obs_dim + 4 > 32)
     int* perm_dev = nullptr; long long perm_cap = 0;
     // global (all-rank) copies used by the replicated fit when world_size > 1
     float* fit_obs = nullptr; int* fit_tstep = nullptr; double* fit_ret = nullptr; long long fit_cap = 0;
@@ -501,13 +502,21 @@ void mjb_destroy(mjb_engine* e) {
     cudaSetDevice(e->cfg.device);
     if (e->stream_vf) cudaStreamSynchronize(e->stream_vf);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    // captured CG graphs hold references on the communicator (NCCL keeps a comm with live graph-captured work alive and
+    // ncclCommDestroy waits for them): the graphs go first
+    for (auto& gph : e->cg_graphs) {
+        if (gph.exec) cudaGraphExecDestroy(gph.exec);
+        for (auto& ev : gph.ev) if (ev) cudaEventDestroy(ev);
+    }
+    e->cg_graphs.clear();
+    cudaDeviceSynchronize();
     if (e->comm) g_nccl.CommDestroy(e->comm);
     void* bufs[] = {e->pnew.theta, e->pnew.prep, e->pnew.in_shift, e->pnew.in_scale, e->pnew.out_shift, e->pnew.out_scale,
                     e->pold.theta, e->pold.prep, e->pold.in_shift, e->pold.in_scale, e->pold.out_shift, e->pold.out_scale,
                     e->prep_tan, e->tc_prep_new, e->tc_prep_tan, e->tc_vscale, e->obs, e->act, e->rew, e->path_off, e->term, e->tstep, e->ret, e->adv, e->base,
                     e->adv_white, e->weights, e->path_ret, e->ll_old, e->mu_old, e->gpartial, e->eval_partial,
                     e->mom_scratch, e->dsc, e->g, e->x, e->r, e->p, e->Fp, e->tmpv, e->idx_dev, e->stage64, e->vf_w,
-                    e->vf_m, e->vf_v, e->vf_wT, e->vf_prep, e->vf_feat, e->vf_ret32, e->vf_consts, e->perm_dev, e->fit_obs, e->fit_tstep, e->fit_ret};
+                    e->vf_m, e->vf_v, e->vf_wT, e->vf_prep, e->vf_feat, e->vf_ret32, e->vf_consts, e->vf_ks, e->perm_dev, e->fit_obs, e->fit_tstep, e->fit_ret};
     for (void* b : bufs) if (b) cudaFree(b);
     if (e->pinned) cudaFreeHost(e->pinned);
     if (e->h_dsc) cudaFreeHost(e->h_dsc);
@@ -515,10 +524,6 @@ void mjb_destroy(mjb_engine* e) {
     for (auto& ev : e->user_ev) if (ev) cudaEventDestroy(ev);
     for (auto& pr : e->fvp_ev) for (auto& ev : pr) if (ev) cudaEventDestroy(ev);
     for (auto& ev : e->fit_ev) if (ev) cudaEventDestroy(ev);
-    for (auto& gph : e->cg_graphs) {
-        if (gph.exec) cudaGraphExecDestroy(gph.exec);
-        for (auto& ev : gph.ev) if (ev) cudaEventDestroy(ev);
-    }
     if (e->stream_vf) { cudaStreamSynchronize(e->stream_vf); cudaStreamDestroy(e->stream_vf); }
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -1200,17 +1205,18 @@ static int vf_fit_launch(mjb_engine* e, const int32_t* perms, int epochs, int ba
     a.w = e->vf_w; a.m = e->vf_m; a.v = e->vf_v; a.wT = e->vf_wT; a.loss_out = nullptr;
     // the tensor-core kernel where the shape allows; every other shape runs the single-CTA fp32-FMA kernel
     const bool use_tc = e->vf_tc_on && vf_tc_supported(a.K, a.H1, a.H2, a.batch);
-    e->vf_sms = 1;
+    e->vf_sms = use_tc ? vf_tc_sms(a.K) : 1;
     e->fit_reads_batch = !use_tc && !e->comm;        // (the replicated multi-GPU fit works on gathered copies)
     if (use_tc) {
         if (N > e->vf_feat_cap) {
             if (e->vf_feat) { cudaFree(e->vf_feat); cudaFree(e->vf_ret32); }
             e->vf_feat_cap = N;
-            CK(e, cudaMalloc(&e->vf_feat, sizeof(float) * (size_t)N * a.K));
+            CK(e, cudaMalloc(&e->vf_feat, sizeof(float) * (size_t)N * vf_tc_feat_pitch(a.K)));
             CK(e, cudaMalloc(&e->vf_ret32, sizeof(float) * (size_t)N));
         }
         if (vf_build_features(a, e->vf_feat, e->vf_ret32, e->stream) != cudaSuccess) FAIL(e, "vf feature kernel launch failed");
         e->launches += 1;
+        if (e->vf_sms > 1 && !e->vf_ks) CK(e, cudaMalloc(&e->vf_ks, vf_tc_scratch_bytes()));
         if (steps > e->vf_consts_cap) {
             if (e->vf_consts) cudaFree(e->vf_consts);
             e->vf_consts_cap = steps + 1024;
@@ -1223,7 +1229,7 @@ static int vf_fit_launch(mjb_engine* e, const int32_t* perms, int epochs, int ba
         a.perm = e->perm_dev + (size_t)ep * N;
         a.step0 = e->vf_step;
         cudaError_t ce;
-        if (use_tc) { ce = launch_vf_fit_tc(a, e->vf_feat, e->vf_ret32, e->vf_consts, fs); e->launches += 2; }
+        if (use_tc) { ce = launch_vf_fit_tc(a, e->vf_feat, e->vf_ret32, e->vf_consts, e->vf_ks, fs); e->launches += 2; }
         else { ce = launch_vf_fit(a, fs); e->launches += 1; }
         if (ce != cudaSuccess) FAIL(e, std::string("vf fit launch (batch<=64, multiple of 4; sizes must fit 220 KB smem): ") + cudaGetErrorString(ce));
         e->vf_step += steps;
@@ -1274,11 +1280,13 @@ int mjb_event_elapsed_ms(mjb_engine* e, int slot_a, int slot_b, float* ms) {
 
 // Developer aid: per-phase clock64 cycle counters of the tensor-core fit kernel.
 int mjb_dev_vf_profile(mjb_engine* e, long long* out16, int enable) {
+    // enable: 1 = arm the counters, 0 = read the head CTA's 16 counters and disarm, 2 = read K-split helper 0's 16 counters
     static long long* dev = nullptr;
-    if (!dev) { CK(e, cudaMalloc(&dev, 16 * sizeof(long long))); }
-    if (enable) { CK(e, cudaMemset(dev, 0, 16 * sizeof(long long))); vf_tc_set_prof(dev); return 0; }
+    if (!dev) { CK(e, cudaMalloc(&dev, 32 * sizeof(long long))); }
+    if (enable == 1) { CK(e, cudaMemset(dev, 0, 32 * sizeof(long long))); vf_tc_set_prof(dev); return 0; }
     CK(e, cudaStreamSynchronize(e->stream));
-    CK(e, cudaMemcpy(out16, dev, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+    CK(e, cudaMemcpy(out16, dev + (enable == 2 ? 16 : 0), 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (enable == 2) return 0;
     vf_tc_set_prof(nullptr);
     return 0;
 }

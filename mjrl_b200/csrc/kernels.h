@@ -128,7 +128,10 @@ cudaError_t vf_build_features(const VfFitArgs& a, float* feat, float* ret32, cud
 // vf_fit_tc.cu : same chain on one SM with tcgen05 (units on the M axis, Adam moments of W2 in TMEM)
 bool vf_tc_supported(int K, int H1, int H2, int batch);
 void vf_tc_set_prof(long long* dev16);
-cudaError_t launch_vf_fit_tc(const VfFitArgs& a, const float* feat, const float* ret32, float4* consts, cudaStream_t s);
+int vf_tc_feat_pitch(int K);             // row pitch (floats) of the feature matrix vf_build_features writes
+int vf_tc_sms(int K);                    // SMs (cluster CTAs) the tensor-core fit occupies: 1 + layer-1 K-split helpers
+size_t vf_tc_scratch_bytes();            // global scratch of the K-split hand-offs
+cudaError_t launch_vf_fit_tc(const VfFitArgs& a, const float* feat, const float* ret32, float4* consts, void* scratch, cudaStream_t s);
 // err = sum((ret - pred)^2) / (sum(ret^2) + 1e-8) pieces: out = {sum err^2, sum ret^2} (fp32 casts like the reference)
 void launch_vf_error(const double* ret, const float* pred, long long n, double* scratch, double* out2, cudaStream_t s);
 

@@ -63,13 +63,33 @@ constexpr int S_TOTAL = S_BAR + 32;
 constexpr uint32_t T_D = 0, T_G1 = 0, T_G2 = 128, T_M = 256, T_V = 384, T_COLS = 512;
 
 struct TcFitArgs {
-    int K, steps;
+    int K, KF, steps;                        // KF: row pitch of feat (K rounded up to 8, zero-filled)
     const float* feat; const float* ret32; const int* perm;
     float reg, beta1, beta2, eps;
     float* w; float* m; float* v;
     const float4* consts;                    // per-step {1/sqrt(1-b2^t), -lr/(1-b1^t), sqrt(1-b2^t), -eps*sqrt(1-b2^t)}
     long long* prof;
+    // ---- K-split layer 1 (input features beyond KP): helper CTAs of the same cluster, hand-offs through L2 ----
+    int nh;                                  // helper CTAs (0 = everything on the head CTA)
+    float* zpart;                            // [2][nh][128 units][64 samples] fp32: layer-1 partial sums (scaled SW*SA)
+    unsigned char* dzop;                     // [2][dz1 hi 16 KB | dz1 lo 16 KB]: the head's dz1^T operand, core-tiled
+    int* flags;                              // [0] head: dz1 of step s published = s+1 ; [1+h] helper h: partial of step s = s+1
 };
+
+// ---- hand-off flags in global memory (release / acquire at gpu scope) ----
+__device__ __forceinline__ void flag_release(int* f, int v) {   // (st.release carries the one gpu-scope fence; cumulative over
+    asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(f), "r"(v) : "memory");   //  the CTA barrier before it)
+}
+// spins until *f >= target; a partner that never arrives is a bug, so the wait is bounded (~2 s) and then traps
+__device__ __forceinline__ void flag_wait_ge(const int* f, int target) {
+    const long long t0 = clock64();
+    int v;
+    for (;;) {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(f) : "memory");
+        if (v >= target) return;
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
 
 struct AdamP { float one_m_b1, b2, one_m_b2, rbc2_sqrt, eps, neg_step, reg; };
 
@@ -170,17 +190,186 @@ __device__ __forceinline__ void gemm2c(uint32_t d, uint32_t ah, uint32_t al, uin
     }
 }
 
+// ---- helper CTA of the K-split (cluster rank 1 + h): owns the 64 input features [KP + 64 h, KP + 64 h + 64) of layer 1 -- their
+// weights (fp16 hi/lo operand + fp32 master), Adam moments, and its own copy of the minibatch columns.  Per step it sends
+// the head the partial pre-activations z1_h = W1_h x_h^T (32 KB fp32 through L2) and, once the head has published dz1
+// (its 32 KB fp16 hi/lo operand, fetched with one TMA bulk copy), computes gW1_h = dz1 x_h and updates its slice.
+// The slice's fp32 master weights and Adam moments live in registers (16 parameters x 3 per thread).  Partial sums travel in a
+// thread-major layout (float4 index (4 cq + j) * 128 + u) so that both sides move 512 contiguous bytes per warp instruction.
+// Shared-memory map of a helper (bytes): W1 operand 2 x 16 KB | X 2 parities x (8 + 8) KB | dz1 16 + 16 KB.
+constexpr int KH = 64;                                   // features per helper
+constexpr int HS_W1H = 0, HS_W1L = HS_W1H + H * KH * 2, HS_X = HS_W1L + H * KH * 2, HS_XB = NB * KH * 2;
+constexpr int HS_DZ = HS_X + 4 * HS_XB, HS_BAR = HS_DZ + 2 * HT_BYTES, HS_TOTAL = HS_BAR + 32;
+constexpr uint32_t HT_Z = 0, HT_G = 64, HT_COLS = 256;
+
+template <bool PROF>
+__device__ __forceinline__ void ks_helper(const TcFitArgs& a, unsigned char* smem, uint32_t* s_tmem, long long* s_prof, int h) {
+    long long t_last = PROF ? clock64() : 0;
+#define KS_PROF(i) do { if (PROF && threadIdx.x == 0) { const long long _t = clock64(); s_prof[i] += _t - t_last; t_last = _t; } } while (0)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + HS_BAR);      // [0] MMA done, [1] dz1 landed
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, cq = warp >> 2, u = 32 * q + lane;
+    const int K = a.K, k0 = KP + KH * h;                              // first feature of this helper
+    if (warp == 0) tmem_alloc(s_tmem, HT_COLS);
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = *s_tmem, sbase = smem_u32(smem);
+    const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
+    const uint32_t rowoff = (uint32_t)((u >> 3) * 128 + (u & 7) * 16);
+    // ---- state slice: W1[u][k0 + 16 cq .. + 15] (natural layout W1[u * K + k]); columns beyond K are zero and stay zero ----
+    float sw[16], sm[16], sv[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int k = k0 + 16 * cq + j;
+        const bool in = k < K;
+        sw[j] = in ? a.w[u * K + k] : 0.0f;
+        sm[j] = in ? a.m[u * K + k] : 0.0f;
+        sv[j] = in ? a.v[u * K + k] : 0.0f;
+    }
+    auto store_w1 = [&]() {
+#pragma unroll
+        for (int g8 = 0; g8 < 2; ++g8) {
+            float x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = SW * sw[8 * g8 + j];
+            const uint32_t o = rowoff + (uint32_t)(2 * cq + g8) * LB128;
+            split8_store(x, smem + HS_W1H + o, smem + HS_W1L + o);
+        }
+    };
+    store_w1();
+    // ---- minibatch gather: thread -> (row gn, 8 features gk .. gk+7 of this helper's 64) ----
+    const int gn = tid >> 3, gk = 8 * (tid & 7);
+    const uint32_t xoff = core_offset(gn, gk, NB);
+    float xr[8];
+    auto load_rows = [&](int idx) {
+        if (k0 + gk < a.KF) {                                        // (row pitch KF is a multiple of 8: whole groups, 32-byte aligned)
+            const float4* p = reinterpret_cast<const float4*>(a.feat + (size_t)idx * a.KF + k0 + gk);
+            const float4 t0 = __ldg(p), t1 = __ldg(p + 1);
+            xr[0] = t0.x; xr[1] = t0.y; xr[2] = t0.z; xr[3] = t0.w; xr[4] = t1.x; xr[5] = t1.y; xr[6] = t1.z; xr[7] = t1.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xr[j] = 0.0f;
+        }
+    };
+    auto stage_x = [&](int par) {
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = SA * xr[j];
+        unsigned char* xb = smem + HS_X + par * 2 * HS_XB;
+        split8_store(x, xb + xoff, xb + HS_XB + xoff);
+    };
+    int i1 = 0, i2 = 0;
+    float4 cst_next = a.consts[0];
+    load_rows(a.perm[gn]);
+    stage_x(0);
+    if (a.steps > 1) i1 = a.perm[NB + gn];
+    if (a.steps > 2) i2 = a.perm[2 * NB + gn];
+    const uint32_t ID_Z = make_idesc_f16(128, NB, false, false);
+    const uint32_t ID_Gc = make_idesc_f16(128, 2 * KH, false, true), ID_G = make_idesc_f16(128, KH, false, true);
+    uint32_t p0 = 0, p1 = 0;
+    AdamP2 ap;
+    ap.one_m_b1 = pk2(1.0f - a.beta1, 1.0f - a.beta1); ap.b2 = pk2(a.beta2, a.beta2);
+    ap.one_m_b2 = pk2(1.0f - a.beta2, 1.0f - a.beta2); ap.eps = pk2(a.eps, a.eps); ap.reg = pk2(a.reg, a.reg);
+    ap.gscale = pk2(1.0f / (SG * SA), 1.0f / (SG * SA));
+    ap.rbc2_sqrt = ap.neg_step = pk2(0.0f, 0.0f);
+    for (int s = 0; s < a.steps; ++s) {
+        fence_proxy_async(); tcgen05_fence_before(); __syncthreads();       // X(s) staged, slice operand current
+        KS_PROF(0);
+        const uint32_t xb = sbase + HS_X + (uint32_t)(s & 1) * 2 * HS_XB;
+        if (tid == 0) {                                              // z1_h^T = W1_h x_h^T
+            tcgen05_fence_after();
+            gemm3<KH / 16>(tmem + HT_Z, sbase + HS_W1H, sbase + HS_W1L, 2 * LB128, LB128, 128,
+                           xb, xb + HS_XB, 2 * LB64, LB64, 128, ID_Z);
+            mma_commit(&bars[0]);
+            KS_PROF(11);
+        }
+        if (s + 1 < a.steps) load_rows(i1);
+        i1 = i2;
+        if (s + 3 < a.steps) i2 = a.perm[(size_t)(s + 3) * NB + gn];
+        const float4 cst = cst_next;
+        if (s + 1 < a.steps) cst_next = a.consts[s + 1];
+        ap.rbc2_sqrt = pk2(cst.x, cst.x); ap.neg_step = pk2(cst.y, cst.y);
+        KS_PROF(1);
+        mbar_wait(&bars[0], p0); p0 ^= 1; tcgen05_fence_after();
+        KS_PROF(2);
+        {                                                            // partial pre-activations -> L2 (fp32, still scaled SW*SA)
+            uint32_t z[16];
+            tmem_ld16(tlane + HT_Z + 16 * cq, z);
+            tmem_ld_wait();
+            float4* dst = reinterpret_cast<float4*>(a.zpart + ((size_t)(s & 1) * a.nh + h) * (H * NB)) + (4 * cq) * H + u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                dst[j * H] = make_float4(__uint_as_float(z[4 * j]), __uint_as_float(z[4 * j + 1]), __uint_as_float(z[4 * j + 2]), __uint_as_float(z[4 * j + 3]));
+        }
+        tcgen05_fence_before();
+        __syncthreads();
+        KS_PROF(3);
+        if (tid == 0) flag_release(a.flags + 1 + h, s + 1);
+        KS_PROF(4);
+        if (s + 1 < a.steps) stage_x((s + 1) & 1);
+        KS_PROF(5);                   // next minibatch while the head works on this one
+        if (tid == 0) {                                              // the head's dz1 operand of this step: one TMA bulk copy
+            flag_wait_ge(a.flags, s + 1);
+            KS_PROF(6);
+            asm volatile("fence.proxy.async.global;\n" ::: "memory");
+            mbar_expect_tx(&bars[1], 2 * HT_BYTES);
+            bulk_g2s(smem + HS_DZ, a.dzop + (size_t)(s & 1) * 2 * HT_BYTES, 2 * HT_BYTES, &bars[1]);
+        }
+        mbar_wait(&bars[1], p1); p1 ^= 1;
+        fence_proxy_async(); tcgen05_fence_before(); __syncthreads();
+        KS_PROF(7);
+        if (tid == 0) {                                              // gW1_h = dz1 x_h  ([hi | lo] columns of x concatenated along N)
+            tcgen05_fence_after();
+            gemm2c<NB / 16>(tmem + HT_G, sbase + HS_DZ, sbase + HS_DZ + HT_BYTES, 2 * LB128, LB128, 128,
+                            xb, 2 * 128, 128, LB64, ID_Gc, ID_G);
+            mma_commit(&bars[0]);
+        }
+        KS_PROF(8);
+        mbar_wait(&bars[0], p0); p0 ^= 1; tcgen05_fence_after();
+        KS_PROF(9);
+        {                                                            // Adam on W1[u][k0 + 16 cq ..]
+            uint32_t g[16], gl[16];
+            tmem_ld16(tlane + HT_G + 16 * cq, g);
+            tmem_ld16(tlane + HT_G + KH + 16 * cq, gl);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; j += 2)
+                adam_apply2(__uint_as_float(g[j]) + __uint_as_float(gl[j]), __uint_as_float(g[j + 1]) + __uint_as_float(gl[j + 1]),
+                            sw[j], sw[j + 1], sm[j], sm[j + 1], sv[j], sv[j + 1], ap);
+            store_w1();
+        }
+        KS_PROF(10);
+    }
+    __syncthreads();
+    if (PROF && a.prof && h == 0 && tid < 16) a.prof[16 + tid] += s_prof[tid];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int k = k0 + 16 * cq + j;
+        if (k < K) { a.w[u * K + k] = sw[j]; a.m[u * K + k] = sm[j]; a.v[u * K + k] = sv[j]; }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, HT_COLS);
+}
+
 // PROF = true instantiates the per-phase clock64 counters (tools/vf_fit_profile.py); the production instance carries none
 // of that code.  Code size matters here: a single resident CTA runs a ~2.7 k-instruction step body 15 624 times, and a
 // body that does not fit the 32 KB instruction cache is re-fetched from L2 every step (the fetch stalls showed up as
 // ~1.3 k unexplained cycles per step that moved with whatever code ran "cold").
-template <bool PROF>
+// KS = true is the cluster form for more than KP input features: CTA 0 is this head, CTAs 1 .. nh run ks_helper.
+template <bool PROF, bool KS>
 __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     float* sf = reinterpret_cast<float*>(smem + S_F32);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S_BAR);
     __shared__ uint32_t s_tmem;
     __shared__ long long s_prof[16];
+    if (KS && blockIdx.x > 0) {                                      // helper CTAs of the K-split (cluster ranks 1 ..)
+        if (threadIdx.x < 16) s_prof[threadIdx.x] = 0;
+        ks_helper<PROF>(a, smem, &s_tmem, s_prof, (int)blockIdx.x - 1);
+        return;
+    }
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, cq = warp >> 2, u = 32 * q + lane;       // TMEM lane = hidden unit u; column quarter cq
     const int K = a.K;
@@ -250,9 +439,9 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
     float xr[4] = {0.f, 0.f, 0.f, 0.f};
     float tt = 0.0f;
     auto load_rows = [&](int idx) {
-        const float* p = a.feat + (size_t)idx * K + gk;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) xr[j] = (gk + j < K) ? p[j] : 0.0f;
+        // feature rows are padded to a multiple of 8 columns (zeros): one aligned 16-byte load per thread
+        const float4 t4 = gk < a.KF ? __ldg(reinterpret_cast<const float4*>(a.feat + (size_t)idx * a.KF + gk)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xr[0] = t4.x; xr[1] = t4.y; xr[2] = t4.z; xr[3] = t4.w;
         if (gk == 0) tt = a.ret32[idx];
     };
     // The minibatch operand is double-buffered (step parity): the rows of step s+1 are staged while the gW2 GEMM of step
@@ -320,6 +509,31 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
             uint32_t z[16];
             tmem_ld16(tlane + T_D + 16 * cq, z);
             tmem_ld_wait();
+            if (KS) {                                                // + the helpers' partial sums over the features beyond KP
+                if (tid == 0) for (int hh = 0; hh < a.nh; ++hh) flag_wait_ge(a.flags + 1 + hh, s + 1);
+                __syncthreads();
+                TC_PROF(15);                                         // (waiting for the helpers' partial sums)
+                // thread-major layout (see ks_helper); helper hh + 1's 64 bytes are in flight while hh's are added
+                const float4* src = reinterpret_cast<const float4*>(a.zpart + (size_t)(s & 1) * a.nh * (H * NB)) + (4 * cq) * H + u;
+                float4 t[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) t[j] = __ldcg(src + j * H);
+                for (int hh = 0; hh < a.nh; ++hh) {                  // fixed order: deterministic
+                    float4 nx[4];
+                    if (hh + 1 < a.nh) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) nx[j] = __ldcg(src + (size_t)(hh + 1) * (H * NB / 4) + j * H);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        z[4 * j] = __float_as_uint(__uint_as_float(z[4 * j]) + t[j].x);
+                        z[4 * j + 1] = __float_as_uint(__uint_as_float(z[4 * j + 1]) + t[j].y);
+                        z[4 * j + 2] = __float_as_uint(__uint_as_float(z[4 * j + 2]) + t[j].z);
+                        z[4 * j + 3] = __float_as_uint(__uint_as_float(z[4 * j + 3]) + t[j].w);
+                        t[j] = nx[j];
+                    }
+                }
+            }
             const float b = sf[F_VEC + 0 * H + u];
             float x[8];
 #pragma unroll
@@ -504,9 +718,16 @@ __global__ void __launch_bounds__(NT, 1) vf_fit_tc_kernel(const TcFitArgs a) {
             const uint32_t o = rowoff + (uint32_t)(2 * cq) * LB128;
             split8_store(x0, smem + S_DH + o, smem + S_DL + o);
             split8_store(x1, smem + S_DH + o + LB128, smem + S_DL + o + LB128);
+            if (KS) {                                                // the same operand rows for the helpers, through L2
+                unsigned char* gd = a.dzop + (size_t)(s & 1) * 2 * HT_BYTES;
+                split8_store(x0, gd + o, gd + HT_BYTES + o);
+                split8_store(x1, gd + o + LB128, gd + HT_BYTES + o + LB128);
+                asm volatile("fence.proxy.async.global;\n" ::: "memory");     // read next by a helper's TMA (async proxy)
+            }
         }
         sync_ops();
         TC_PROF(9);
+        if (KS && tid == 0) flag_release(a.flags, s + 1);            // every thread's dz1 rows are written (barrier above)
         if (tid == 0) {                                              // gW1 = dz1 x -> bar 0, under the second Adam half of W2
             tcgen05_fence_after();
             gemm2c<NB / 16>(tmem + T_G1, sbase + S_DH, sbase + S_DL, 2 * LB128, LB128, 128,
@@ -600,14 +821,17 @@ long long* g_tc_prof = nullptr;
 // fp32 feature matrix of the whole batch, in the reference's dtypes (mlp_baseline.py:36-58): fp64 feature map, then
 // .astype(float32); built once per fit, all epochs gather minibatch rows from it.
 __global__ void vf_features_kernel(const float* __restrict__ obs, const int* __restrict__ tstep,
-                                   const double* __restrict__ returns, long long n, int obs_dim, int K,
+                                   const double* __restrict__ returns, long long n, int obs_dim, int K, int KF,
                                    float* __restrict__ feat, float* __restrict__ ret32) {
-    const long long total = n * K;
+    // rows of KF = round_up(K, 8) columns, the pad zero-filled: the fit kernels gather them with aligned 16-byte loads
+    const long long total = n * KF;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / K;
-        const int k = (int)(i - r * K);
+        const long long r = i / KF;
+        const int k = (int)(i - r * KF);
         float val;
-        if (k < obs_dim) {
+        if (k >= K) {
+            val = 0.0f;
+        } else if (k < obs_dim) {
             double x = (double)obs[r * obs_dim + k];
             x = fmin(fmax(x, -10.0), 10.0) / 10.0;
             val = (float)x;
@@ -624,26 +848,57 @@ __global__ void vf_features_kernel(const float* __restrict__ obs, const int* __r
 
 }  // namespace
 
+int vf_tc_feat_pitch(int K) { return (K + 7) & ~7; }
+
 cudaError_t vf_build_features(const VfFitArgs& v, float* feat, float* ret32, cudaStream_t s) {
-    vf_features_kernel<<<148 * 8, 256, 0, s>>>(v.obs, v.tstep, v.returns, v.n, v.obs_dim, v.K, feat, ret32);
+    vf_features_kernel<<<148 * 8, 256, 0, s>>>(v.obs, v.tstep, v.returns, v.n, v.obs_dim, v.K, vf_tc_feat_pitch(v.K), feat, ret32);
     return cudaGetLastError();
 }
 
 void vf_tc_set_prof(long long* dev16) { g_tc_prof = dev16; }
 
-bool vf_tc_supported(int K, int H1, int H2, int batch) { return batch == NB && H1 == H && H2 == H && K >= 1 && K <= KP; }
+constexpr int KS_MAX_HELPERS = 7;                                   // portable cluster size 8 = head + 7 helpers
+static int ks_helpers(int K) { return K <= KP ? 0 : (K - KP + KH - 1) / KH; }
+bool vf_tc_supported(int K, int H1, int H2, int batch) {
+    return batch == NB && H1 == H && H2 == H && K >= 1 && ks_helpers(K) <= KS_MAX_HELPERS;
+}
+int vf_tc_sms(int K) { return 1 + ks_helpers(K); }
+// scratch of the K-split hand-offs: flags (256 B) | dz1 operand 2 x 32 KB | partial sums 2 x 7 x 32 KB
+size_t vf_tc_scratch_bytes() { return 256 + 2 * 2 * (size_t)HT_BYTES + 2 * (size_t)KS_MAX_HELPERS * H * NB * 4; }
 
-cudaError_t launch_vf_fit_tc(const VfFitArgs& v, const float* feat, const float* ret32, float4* consts, cudaStream_t s) {
+cudaError_t launch_vf_fit_tc(const VfFitArgs& v, const float* feat, const float* ret32, float4* consts, void* scratch, cudaStream_t s) {
     tc_adam_consts_kernel<<<(v.steps + 255) / 256, 256, 0, s>>>(consts, v.steps, v.step0, v.lr, v.beta1, v.beta2, v.eps);
     TcFitArgs a;
-    a.K = v.K; a.steps = v.steps; a.feat = feat; a.ret32 = ret32; a.perm = v.perm;
+    a.K = v.K; a.KF = vf_tc_feat_pitch(v.K); a.steps = v.steps; a.feat = feat; a.ret32 = ret32; a.perm = v.perm;
     a.reg = v.reg; a.beta1 = v.beta1; a.beta2 = v.beta2; a.eps = v.eps;
     a.w = v.w; a.m = v.m; a.v = v.v; a.consts = consts; a.prof = g_tc_prof;
-    auto kern = a.prof ? vf_fit_tc_kernel<true> : vf_fit_tc_kernel<false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S_TOTAL);
+    a.nh = ks_helpers(v.K);
+    a.flags = nullptr; a.dzop = nullptr; a.zpart = nullptr;
+    if (a.nh == 0) {
+        auto kern = a.prof ? vf_fit_tc_kernel<true, false> : vf_fit_tc_kernel<false, false>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S_TOTAL);
+        if (e != cudaSuccess) return e;
+        kern<<<1, NT, S_TOTAL, s>>>(a);
+        return cudaGetLastError();
+    }
+    // K-split: one cluster of 1 + nh CTAs (co-scheduled, so the flag waits between them cannot deadlock)
+    unsigned char* sc = static_cast<unsigned char*>(scratch);
+    a.flags = reinterpret_cast<int*>(sc);
+    a.dzop = sc + 256;
+    a.zpart = reinterpret_cast<float*>(sc + 256 + 2 * 2 * (size_t)HT_BYTES);
+    cudaError_t e = cudaMemsetAsync(a.flags, 0, 256, s);
     if (e != cudaSuccess) return e;
-    kern<<<1, NT, S_TOTAL, s>>>(a);
-    return cudaGetLastError();
+    auto kern = a.prof ? vf_fit_tc_kernel<true, true> : vf_fit_tc_kernel<false, true>;
+    constexpr int SMEM = S_TOTAL > HS_TOTAL ? S_TOTAL : HS_TOTAL;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1 + a.nh); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = SMEM; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1 + a.nh; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
 }  // namespace mjb

@@ -19,6 +19,8 @@ from mjrl_b200.parallel import shard_bounds  # noqa: E402
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(240, exit=True)      # a stuck collective must end with a traceback, not a hung box
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))

@@ -1,4 +1,7 @@
-"""Developer tool: per-phase cycle breakdown of the tensor-core fit kernel (clock64 on thread 0)."""
+"""Developer tool: per-phase cycle breakdown of the tensor-core fit kernel (clock64 on thread 0 of the head CTA).
+
+    python tools/vf_fit_profile.py [obs_dim]     (17 = cfg3; 39 = cfg4, one K-split helper; 376 = cfg5, six helpers)
+"""
 import ctypes as C
 import sys
 import time
@@ -8,7 +11,7 @@ import numpy as np
 sys.path.insert(0, ".")
 from mjrl_b200.engine import Engine  # noqa: E402
 
-N, obs_dim = 200000, 17
+N, obs_dim = 200000, (int(sys.argv[1]) if len(sys.argv) > 1 else 17)
 rng = np.random.RandomState(0)
 eng = Engine(obs_dim, 6, (128, 128), max_samples=N + 8, max_paths=256)
 eng.upload_flat(rng.randn(N, obs_dim), rng.randn(N, 6), rng.randn(N), np.full(200, 1000, np.int32), np.zeros(200, np.uint8))
@@ -24,19 +27,29 @@ for cl, mp in ((1, True),):
     perm = rng.permutation(N).astype(np.int32)
     eng.vf_fit(perm, 64, 1e-3, 1e-3)
     eng.vf_fit(perm, 64, 1e-3, 1e-3)
-    print("production instance (no counters): %.3f us per Adam step (CUDA events around the kernel, %d steps)" % (
+    print("obs_dim %d:" % obs_dim, "production instance (no counters): %.3f us per Adam step (CUDA events around the kernel, %d steps)" % (
         eng.last_fit_ms() * 1e3 / (N // 64 - 1), N // 64 - 1))
     eng.lib.mjb_dev_vf_profile(eng.h, None, 1)
     t0 = time.time()
     eng.vf_fit(perm, 64, 1e-3, 1e-3)
     dt = time.time() - t0
     out = (C.c_longlong * 16)()
+    hout = (C.c_longlong * 16)()
+    eng.lib.mjb_dev_vf_profile(eng.h, hout, 2)
     eng.lib.mjb_dev_vf_profile(eng.h, out, 0)
     steps = N // 64 - 1
-    tot = sum(out[:15])
+    tot = sum(out[:16])
     print("vf_fit_tc_kernel: %.2f us/step wall, %d cycles/step" % (dt / steps * 1e6, tot // steps))
-    names = names_tc + ["(top-of-step barrier: waiting for the slowest warp)", "(issue of the 6 layer-1 MMAs; 'issue L1' above is what follows)"]
+    names = names_tc + ["(top-of-step barrier: waiting for the slowest warp)", "(issue of the 6 layer-1 MMAs; 'issue L1' above is what follows)",
+                        "(K-split: waiting for the helpers' partial sums; 'E1' above is what follows)"]
     for i, n in enumerate(names):
         if n == "-":
             continue
         print("   %-34s %7d cyc  %5.1f%%" % (n, out[i] // steps, 100.0 * out[i] / tot))
+    if obs_dim + 4 > 32:
+        hn = ["top-of-step fence + barrier", "issue z MMAs, gather loads", "wait z", "partial -> L2 + barrier", "release flag (fence)",
+              "stage next X", "wait head's dz1 flag", "proxy fence, TMA 32 KB, barrier", "issue gW1", "wait gW1", "Adam slice", "(issue of the 12 z MMAs; 'issue z MMAs' above is what follows)"]
+        htot = sum(hout[:12])
+        print("K-split helper 0: %d cycles/step" % (htot // steps))
+        for i, n in enumerate(hn):
+            print("   %-34s %7d cyc  %5.1f%%" % (n, hout[i] // steps, 100.0 * hout[i] / htot))
