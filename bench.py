@@ -333,7 +333,9 @@ def workload_config(cfg, args, world):
     return {"workload": cfg["name"], "obs_dim": cfg["obs"], "act_dim": cfg["act"], "hidden": list(cfg["hidden"]),
             "n_traj": cfg["n_traj"], "horizon": cfg["horizon"], "timesteps": cfg["n_traj"] * cfg["horizon"],
             "algo": cfg["algo"], "cg_iters": CG_ITERS, "damping": DAMPING, "vf_epochs": VF["epochs"],
-            "parallelism": "dp%d (trajectory shards, NCCL all-reduce of flat gradient + each FVP)" % world,
+            "parallelism": "dp%d (trajectory shards; every FVP ends in an all-reduce of d floats: fused peer-memory kernel over "
+                           "NVLink when the ranks can map each other, else ncclAllReduce -- see fvp_allreduce; NCCL for the flat "
+                           "gradient and the scalar statistics)" % world,
             "cache": "batch < L2 on purpose of the workload: obs stays L2-resident across the 10 CG FVPs of a step as in "
                      "production; every step also streams the 1e6-row fit gather + GAE arrays (> L2 in total)"}
 
@@ -576,6 +578,9 @@ def run_gpu(args, cfg, rank, world, local_rank):
                     "api": "mjrl_b200.algos.%s.update_from_paths(paths) on host float64 path dicts (per rank shard)"
                            % {"npg": "npg_cg.NPG", "trpo": "trpo.TRPO", "dapg": "dapg.DAPG"}[cfg["algo"]]},
             "fvp_per_sec": fvp_per_sec, "fvp_ms_in_cg": cg_ms / CG_ITERS, "fvp_kernel_ms": fvp_ms_kernel,
+            "fvp_allreduce": ("none (1 rank)" if world == 1 else
+                              "p2p (reduce + NVLink scatter + rank-ordered sum in one kernel)" if getattr(eng, "p2p", False)
+                              else "nccl"),
             "wall_ms_per_step": wall / args.steps * 1e3, "phase_ms": phase, "trpo_backtracks": backtracks,
             "fit_us_per_adam_step": fit_us, "fit_adam_steps": fit_steps,
             "roofline": roof, "roofline_hbm": hbm, "cpu_baseline": cpu, "trpo_backtrack_check": bt_check}

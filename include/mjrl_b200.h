@@ -75,6 +75,15 @@ int  mjb_synchronize(mjb_engine* e);
  * rank calls mjb_comm_init.  All reductions below then all-reduce across ranks.         */
 int  mjb_comm_unique_id(void* id128);
 int  mjb_comm_init(mjb_engine* e, const void* id128);
+/* All-reduce over NVLink peer memory for the Fisher-vector products (one fused kernel: partial reduction + scatter to the
+ * peers + rank-ordered sum; replaces reduce kernel + ncclAllReduce, SURVEY 8e collective (3)).  Every rank exports the
+ * CUDA IPC handle (64 bytes) of its exchange buffer, the host side all-gathers them in rank order, every rank imports
+ * the world x 64 bytes; mjb_p2p_enable(e, 1) must only be called once EVERY rank imported successfully (returns the
+ * resulting state, 0 = NCCL path).  mjb_p2p_calls: fused all-reduces executed so far.                          */
+int  mjb_p2p_export(mjb_engine* e, void* handle64);
+int  mjb_p2p_import(mjb_engine* e, const void* handles);
+int  mjb_p2p_enable(mjb_engine* e, int on);
+long long mjb_p2p_calls(mjb_engine* e);
 
 /* ---- trajectories in (samplers/core.py:85-92 path dicts; algos/batch_reinforce.py:180-182 concat) */
 /* Per-path HOST pointers to float64 arrays exactly as the sampler delivers them: obs[i] -> (len[i],

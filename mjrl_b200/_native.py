@@ -49,6 +49,10 @@ _SIGNATURES = {
     "mjb_synchronize": (C.c_int, [_P]),
     "mjb_comm_unique_id": (C.c_int, [_P]),
     "mjb_comm_init": (C.c_int, [_P, _P]),
+    "mjb_p2p_export": (C.c_int, [_P, _P]),
+    "mjb_p2p_import": (C.c_int, [_P, _P]),
+    "mjb_p2p_enable": (C.c_int, [_P, C.c_int]),
+    "mjb_p2p_calls": (C.c_longlong, [_P]),
     "mjb_batch_upload": (C.c_int, [_P, C.c_int, C.c_int32, _P, _P, _P, _P, _P]),
     "mjb_batch_upload_flat": (C.c_int, [_P, C.c_int, C.c_int32, _P, _P, _P, _P, _P]),
     "mjb_batch_upload_rollouts": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, C.c_int, _P, _P]),

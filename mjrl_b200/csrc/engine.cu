@@ -115,6 +115,13 @@ struct mjb_engine {
     int vf_sms = 1;           // SMs the fit kernel in flight occupies
     float4* vf_consts = nullptr; int vf_consts_cap = 0;   // per-step Adam constants of the fit kernels
     void* vf_ks = nullptr;    // hand-off scratch of the K-split tensor-core fit (obs_dim + 4 > 32)
+    // ---- all-reduce over NVLink peer memory (p2p.cu): exchange buffer of this rank, peers' buffers opened through CUDA IPC
+    unsigned long long* p2p_buf = nullptr; size_t p2p_bytes = 0;
+    std::vector<void*> p2p_peer;              // [world] mapped base pointers (own buffer at [rank])
+    unsigned long long** p2p_peer_dev = nullptr; int* p2p_seq = nullptr;
+    long long p2p_slot = 0;
+    bool p2p_ready = false, p2p_on = false;
+    long long p2p_calls = 0;
     int* perm_dev = nullptr; long long perm_cap = 0;
     // global (all-rank) copies used by the replicated fit when world_size > 1
     float* fit_obs = nullptr; int* fit_tstep = nullptr; double* fit_ret = nullptr; long long fit_cap = 0;
@@ -130,7 +137,7 @@ struct mjb_engine {
     // ---- CUDA graphs of the device-resident CG loop (one per distinct launch shape)
     struct CgGraph {
         long long n = 0; const int* idx = nullptr; long long n_idx = 0; int iters = 0; float damping = 0.f, tol = 0.f;
-        int sms = 0; bool tc = false; cudaGraphExec_t exec = nullptr;
+        int sms = 0; bool tc = false, p2p = false; cudaGraphExec_t exec = nullptr;
         std::vector<cudaEvent_t> ev;              // 2 per iteration: around the FVP tile kernel
     };
     std::vector<CgGraph> cg_graphs;
@@ -279,6 +286,28 @@ int ensure_old_cache(mjb_engine* e, long long rows) {
     return 0;
 }
 
+// Tail of every Fisher-vector product: sum of the per-CTA partials (+ the data-free log_std block), summed over the ranks.
+// With peer memory set up (mjb_p2p_import) this is ONE kernel -- partial reduction, NVLink scatter, flag exchange, rank-
+// ordered sum (p2p.cu); otherwise the reduction kernel followed by ncclAllReduce.
+int fvp_reduce(mjb_engine* e, int grid, bool subsample, const float* v, float* out, const float* vscale) {
+    const double* scale = e->dsc + (subsample ? DS_SCALE_SUB : DS_SCALE);
+    if (e->comm && e->p2p_on) {
+        P2PReduceArgs a;
+        a.partial = e->gpartial; a.grid = grid; a.stride = e->gstride; a.d = e->d;
+        a.scale_dev = scale; a.theta = e->pnew.theta; a.v = v; a.tLS = e->tLS; a.fvp_ls_block = 1; a.vscale = vscale;
+        a.out = out; a.peers = e->p2p_peer_dev; a.world = e->cfg.world_size; a.rank = e->cfg.rank;
+        a.cta_seq = e->p2p_seq; a.slot_words = e->p2p_slot;
+        if (launch_reduce_allreduce_p2p(a, e->stream) != cudaSuccess) FAIL(e, "p2p reduce launch failed");
+        e->launches += 1;
+        e->p2p_calls += 1;
+        return 0;
+    }
+    launch_reduce_partials(e->gpartial, grid, e->gstride, e->d, scale, out, e->pnew.theta, v, e->tLS, 1, vscale, e->stream);
+    e->launches += 1;
+    CK(e, cudaGetLastError());
+    return allreduce(e, out, e->d, ncclFloat);
+}
+
 // F v (undamped, all-reduced) into out.  v, out: device pointers of d floats.
 // have_vscale: e->tc_vscale already holds the power-of-two scale of v (written by cg_init / cg_update).
 // ev0/ev1: events recorded around the tile kernel (the FVP ring slot, or a graph's own pair while capturing).
@@ -310,11 +339,8 @@ int fvp_device(mjb_engine* e, const float* v, const int* idx, long long n_idx, f
                             e->pnew.out_scale, e->obs, idx, n, e->gpartial, e->gstride, grid, e->stream);
         if (ce != cudaSuccess) FAIL(e, std::string("fvp_tc launch: ") + cudaGetErrorString(ce));
         CK(e, cudaEventRecordWithFlags(ev1, e->stream, evflag));
-        launch_reduce_partials(e->gpartial, grid, e->gstride, e->d, e->dsc + (idx ? DS_SCALE_SUB : DS_SCALE), out,
-                               e->pnew.theta, v, e->tLS, 1, e->tc_vscale, e->stream);
-        e->launches += 3;
-        CK(e, cudaGetLastError());
-        return allreduce(e, out, e->d, ncclFloat);
+        e->launches += 2;
+        return fvp_reduce(e, grid, idx != nullptr, v, out, e->tc_vscale);
     }
     if (e->linear) launch_prep_linear(v, e->LL, e->prep_tan, e->stream);
     else launch_prep_mlp(v, e->PL, e->prep_tan, e->stream);
@@ -324,11 +350,7 @@ int fvp_device(mjb_engine* e, const float* v, const int* idx, long long n_idx, f
     int grid = run_policy(e, MODE_FVP, e->pnew, e->prep_tan, n, idx, nullptr, 0);
     if (grid < 0) return -1;
     CK(e, cudaEventRecordWithFlags(ev1, e->stream, evflag));
-    launch_reduce_partials(e->gpartial, grid, e->gstride, e->d, e->dsc + (idx ? DS_SCALE_SUB : DS_SCALE), out,
-                           e->pnew.theta, v, e->tLS, 1, nullptr, e->stream);
-    e->launches += 1;
-    CK(e, cudaGetLastError());
-    return allreduce(e, out, e->d, ncclFloat);
+    return fvp_reduce(e, grid, idx != nullptr, v, out, nullptr);
 }
 
 int set_subsample_scale(mjb_engine* e, long long n_idx_local) {
@@ -438,7 +460,7 @@ int cg_device(mjb_engine* e, const float* b, int iters, float damping, float tol
     mjb_engine::CgGraph* hit = nullptr;
     for (auto& gph : e->cg_graphs)
         if (gph.n == n && gph.idx == idx_dev && gph.n_idx == n_idx && gph.iters == iters && gph.damping == damping &&
-            gph.tol == tol && gph.sms == sms && gph.tc == tc) { hit = &gph; break; }
+            gph.tol == tol && gph.sms == sms && gph.tc == tc && gph.p2p == e->p2p_on) { hit = &gph; break; }
     if (!hit) {
         if (e->cg_graphs.size() >= 8) {                       // shapes keep changing: drop the oldest
             auto& old = e->cg_graphs.front();
@@ -448,7 +470,7 @@ int cg_device(mjb_engine* e, const float* b, int iters, float damping, float tol
         }
         mjb_engine::CgGraph gph;
         gph.n = n; gph.idx = idx_dev; gph.n_idx = n_idx; gph.iters = iters; gph.damping = damping; gph.tol = tol;
-        gph.sms = sms; gph.tc = tc;
+        gph.sms = sms; gph.tc = tc; gph.p2p = e->p2p_on;
         gph.ev.assign((size_t)2 * iters, nullptr);
         for (auto& ev : gph.ev) CK(e, cudaEventCreate(&ev));
         // occupancy queries / attribute setters of the kernels must not run for the first time inside a capture
@@ -511,6 +533,11 @@ void mjb_destroy(mjb_engine* e) {
     e->cg_graphs.clear();
     cudaDeviceSynchronize();
     if (e->comm) g_nccl.CommDestroy(e->comm);
+    for (int p = 0; p < (int)e->p2p_peer.size(); ++p)
+        if (p != e->cfg.rank && e->p2p_peer[p]) cudaIpcCloseMemHandle(e->p2p_peer[p]);
+    if (e->p2p_buf) cudaFree(e->p2p_buf);
+    if (e->p2p_peer_dev) cudaFree(e->p2p_peer_dev);
+    if (e->p2p_seq) cudaFree(e->p2p_seq);
     void* bufs[] = {e->pnew.theta, e->pnew.prep, e->pnew.in_shift, e->pnew.in_scale, e->pnew.out_shift, e->pnew.out_scale,
                     e->pold.theta, e->pold.prep, e->pold.in_shift, e->pold.in_scale, e->pold.out_shift, e->pold.out_scale,
                     e->prep_tan, e->tc_prep_new, e->tc_prep_tan, e->tc_vscale, e->obs, e->act, e->rew, e->path_off, e->term, e->tstep, e->ret, e->adv, e->base,
@@ -648,6 +675,59 @@ int mjb_comm_init(mjb_engine* e, const void* id128) {
     NK(e, g_nccl.CommInitRank(&e->comm, e->cfg.world_size, id, e->cfg.rank));
     return 0;
 }
+
+// ---- all-reduce over NVLink peer memory: every rank exports its exchange buffer as a CUDA IPC handle, the host side
+// all-gathers the 64-byte handles (torch.distributed) and every rank imports all of them.
+int mjb_p2p_export(mjb_engine* e, void* handle64) {
+    if (e->cfg.world_size == 1) FAIL(e, "mjb_p2p_export: single-rank engine");
+    CK(e, cudaSetDevice(e->cfg.device));
+    if (!e->p2p_buf) {
+        const int ctas = (e->d + 127) / 128;
+        e->p2p_slot = ((long long)e->d + 31) / 32 * 32;
+        e->p2p_bytes = (size_t)2 * e->cfg.world_size * e->p2p_slot * sizeof(unsigned long long);
+        CK(e, cudaMalloc(&e->p2p_buf, e->p2p_bytes));
+        CK(e, cudaMemset(e->p2p_buf, 0, e->p2p_bytes));       // call numbers start at 1: a zeroed word is "not yet"
+        CK(e, cudaMalloc(&e->p2p_seq, sizeof(int) * ctas));
+        CK(e, cudaMemset(e->p2p_seq, 0, sizeof(int) * ctas));
+        CK(e, cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    CK(e, cudaIpcGetMemHandle(&h, e->p2p_buf));
+    static_assert(sizeof(h) == 64, "CUDA IPC handles are 64 bytes");
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+
+int mjb_p2p_import(mjb_engine* e, const void* handles /* world x 64 bytes, rank order */) {
+    if (!e->p2p_buf) FAIL(e, "mjb_p2p_import: call mjb_p2p_export first");
+    CK(e, cudaSetDevice(e->cfg.device));
+    const int W = e->cfg.world_size;
+    e->p2p_peer.assign(W, nullptr);
+    for (int p = 0; p < W; ++p) {
+        if (p == e->cfg.rank) { e->p2p_peer[p] = e->p2p_buf; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const unsigned char*>(handles) + 64 * p, 64);
+        const cudaError_t ce = cudaIpcOpenMemHandle(&e->p2p_peer[p], h, cudaIpcMemLazyEnablePeerAccess);
+        if (ce != cudaSuccess) {
+            e->p2p_peer[p] = nullptr;
+            cudaGetLastError();
+            FAIL(e, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(p) + "): " + cudaGetErrorString(ce));
+        }
+    }
+    if (!e->p2p_peer_dev) CK(e, cudaMalloc(&e->p2p_peer_dev, sizeof(void*) * W));
+    CK(e, cudaMemcpy(e->p2p_peer_dev, e->p2p_peer.data(), sizeof(void*) * W, cudaMemcpyHostToDevice));
+    e->p2p_ready = true;
+    return 0;
+}
+
+// on = 1 only takes effect after a successful import ON EVERY RANK (the caller agrees on that: a rank on NCCL and a rank
+// on peer memory would wait for each other forever).  Returns the resulting state.
+int mjb_p2p_enable(mjb_engine* e, int on) {
+    e->p2p_on = on != 0 && e->p2p_ready && e->comm != nullptr;
+    return e->p2p_on ? 1 : 0;
+}
+
+long long mjb_p2p_calls(mjb_engine* e) { return e->p2p_calls; }
 
 // ---------------------------------------------------------------------------------------------- batch
 int mjb_vf_fit_end(mjb_engine* e, double* err_after);

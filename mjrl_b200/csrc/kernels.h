@@ -80,6 +80,18 @@ void launch_reduce_partials(const float* partial, int grid, long long stride, in
                             float* out, const float* theta, const float* v, int tLS, int fvp_ls_block,
                             const float* vscale2, cudaStream_t s);
 void launch_reduce_eval(const double* partial, int grid, double* out2, cudaStream_t s);
+
+// ---- p2p.cu : the same reduction fused with the all-reduce over NVLink peer memory (one kernel, no NCCL call)
+struct P2PReduceArgs {
+    const float* partial; int grid; long long stride; int d;      // as launch_reduce_partials
+    const double* scale_dev; const float* theta; const float* v; int tLS; int fvp_ls_block; const float* vscale;
+    float* out;
+    unsigned long long* const* peers;   // device array [world]: exchange buffer of every rank (own one included), peer-mapped:
+    int world, rank;                    //   64-bit words {call number : value} [2 parities][world][slot_words]
+    int* cta_seq;                       // [ceil(d / 128)] per-CTA call counters (own memory)
+    long long slot_words;
+};
+cudaError_t launch_reduce_allreduce_p2p(const P2PReduceArgs& a, cudaStream_t s);
 // CG state lives on device: st = {rdotr, done_flag(as double), iters_run, g.x}
 // vscale2 (nullable): also emit the power-of-two scale {s, 1/s} of the new search direction p (tensor-core FVP)
 void launch_cg_init(const float* b, float* x, float* r, float* p, int d, double* st, float* vscale2, cudaStream_t s);

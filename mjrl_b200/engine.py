@@ -26,6 +26,7 @@ class Engine:
     def __init__(self, obs_dim, act_dim, hidden=(64, 64), vf_hidden=(128, 128), min_log_std=-3.0,
                  max_samples=1 << 16, max_paths=4096, device=0, world_size=1, rank=0):
         self.lib = _native.load()
+        self.p2p = False          # fused peer-memory all-reduce of the Fisher products (set by init_p2p, world_size > 1)
         hidden = tuple(int(h) for h in hidden)
         if len(hidden) not in (0, 2):
             raise NotImplementedError("mjrl_b200 supports LinearPolicy (no hidden layer) and 2-hidden-layer MLPs "
@@ -97,6 +98,31 @@ class Engine:
             raise MjbError("mjb_comm_unique_id: " + self.lib.mjb_last_error(None).decode())
         raw = broadcast_bytes(bytes(buf), 128, src=0, device=self.cfg.device)
         self._ck(self.lib.mjb_comm_init(self.h, C.c_char_p(raw)), "comm_init")
+        self.init_p2p()
+
+    def init_p2p(self):
+        """All-reduce of the Fisher-vector products over NVLink peer memory (csrc/p2p.cu): the ranks exchange the CUDA IPC
+        handles of their exchange buffers; the fused kernel is switched on only if EVERY rank could map every peer
+        (otherwise all ranks stay on ncclAllReduce).  MJRL_B200_P2P=0 keeps NCCL."""
+        import os
+        from .parallel import all_gather_bytes, all_ranks_agree
+        self.p2p = False
+        want = os.environ.get("MJRL_B200_P2P", "1") != "0"
+        h = (C.c_char * 64)()
+        ok = want and self.lib.mjb_p2p_export(self.h, h) == 0
+        handles = all_gather_bytes(bytes(h), 64, device=self.cfg.device)
+        if ok:
+            ok = self.lib.mjb_p2p_import(self.h, C.c_char_p(b"".join(handles))) == 0
+        if all_ranks_agree(ok, device=self.cfg.device):
+            self.p2p = bool(self.lib.mjb_p2p_enable(self.h, 1))
+
+    def set_p2p(self, on):
+        """Switch between the fused peer-memory all-reduce and ncclAllReduce (collective: call on every rank)."""
+        self.p2p = bool(self.lib.mjb_p2p_enable(self.h, 1 if on else 0))
+        return self.p2p
+
+    def p2p_calls(self):
+        return int(self.lib.mjb_p2p_calls(self.h))
 
     # ------------------------------------------------------------------ trajectories
     def upload_paths(self, paths, which=ROLLOUT):

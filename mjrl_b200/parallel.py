@@ -44,6 +44,29 @@ def broadcast_bytes(payload, nbytes, src=0, device=None):
     return bytes(t.cpu().numpy().tobytes())
 
 
+def all_gather_bytes(buf, n, device=None):
+    """Every rank contributes n bytes; returns the list of all ranks' byte strings in rank order."""
+    import torch
+    import torch.distributed as dist
+    t = torch.frombuffer(bytearray(buf[:n].ljust(n, b"\0")), dtype=torch.uint8).clone()
+    if dist.get_backend() == "nccl":
+        t = t.cuda(device)
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [bytes(o.cpu().numpy().tobytes()) for o in out]
+
+
+def all_ranks_agree(flag, device=None):
+    """True iff `flag` is true on every rank."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32)
+    if dist.get_backend() == "nccl":
+        t = t.cuda(device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(int(t.cpu()[0]) == 1)
+
+
 def local_subsample(global_idx, bounds_samples, rank):
     """hvp_sample_frac < 1 under data parallelism: the host draws global sample indices once; each rank keeps the
     ones inside its own sample range, rebased to local row numbers."""

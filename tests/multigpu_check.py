@@ -47,9 +47,28 @@ def main():
         np.testing.assert_allclose([st.mean_return, st.std_return, st.min_return, st.max_return], g["base_stats"], rtol=1e-10)
         np.testing.assert_allclose(eng.adv_white(), g["adv_white"][off:off + n_loc].astype(np.float32), atol=1e-6, rtol=0)
         assert rel(eng.vpg(), g["vpg"]) < 1e-5
-        assert rel(eng.fvp(g["fvp_vec"], m["damping"]), g["fvp_out"]) < 1e-5
+        # the Fisher product's all-reduce: fused peer-memory kernel (default when every rank could map its peers) against
+        # ncclAllReduce -- same local sums, rank-ordered vs NCCL's order of additions
+        assert eng.p2p, "peer-memory all-reduce not enabled (cudaIpcOpenMemHandle failed?)"
+        c0 = eng.p2p_calls()
+        f_p2p = eng.fvp(g["fvp_vec"], m["damping"])
+        assert eng.p2p_calls() == c0 + 1
+        assert rel(f_p2p, g["fvp_out"]) < 1e-5
+        assert eng.set_p2p(False) is False
+        f_nccl = eng.fvp(g["fvp_vec"], m["damping"])
+        assert eng.p2p_calls() == c0 + 1
+        assert rel(f_p2p, f_nccl) < 2e-7, rel(f_p2p, f_nccl)
+        x_nccl = eng.cg(g["vpg"], iters=m["cg_iters"], damping=m["damping"])
+        assert eng.set_p2p(True) is True
         x = eng.cg(g["vpg"], iters=m["cg_iters"], damping=m["damping"])
+        assert eng.p2p_calls() >= c0 + 2
         assert one_minus_cos(x, g["cg_x"]) < 1e-6
+        assert one_minus_cos(x, x_nccl) < 1e-9
+        t = torch.from_numpy(x.copy()).cuda()                       # bit-identical CG solution on every rank
+        lo, hi = t.clone(), t.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert torch.equal(lo, hi)
         st = eng.step("npg", step_size=m["npg_step"], cg_iters=m["cg_iters"], damping=m["damping"])
         new = eng.get_params()
         assert rel(new, g["npg_theta"]) < 1e-4, rel(new, g["npg_theta"])
