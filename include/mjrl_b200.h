@@ -218,6 +218,20 @@ int  mjb_vf_fit_timing(mjb_engine* e, float* last_ms);
 /* ---- developer aids (used by tools/, not by the Python mirror) ---------------------------------- */
 /* per-phase clock64 counters of the tensor-core fit kernel / of the linear-policy FVP kernel: enable = 1 arms the
  * counters, enable = 0 reads them back (16 values each) and disarms. */
+/* ---- ridge-regression baselines on the resident batch (replaces the N-dependent part of LinearBaseline / QuadraticBaseline:
+ * baselines/linear_baseline.py:11-60, baselines/quadratic_baseline.py:11-68).  kind 0 = linear features
+ * [clip(o)/10 | 1 | al..al^4] (K = obs_dim + 5), kind 1 = linear + all products o_i o_j, i <= j (K = n + n(n+1)/2 + 5), al =
+ * time step / 1000; float64 arithmetic on the fp32-resident observations.
+ *   mjb_ridge_features : K.
+ *   mjb_ridge_gram     : out[(K+1) x (K+1)] (host doubles, row-major) = Gram matrix of [F | returns], summed over the ranks:
+ *                        F^T F = out[:K,:K], F^T y = out[:K,K], y^T y = out[K,K].  The K x K solve stays with the caller
+ *                        (the reference's np.linalg.lstsq retry loop).
+ *   mjb_ridge_predict  : F c for every resident sample into the baseline buffer (read by mjb_compute_advantages, returned by
+ *                        mjb_batch_get); sq_err (nullable) = sum over all ranks of (returns - F c)^2.                       */
+int  mjb_ridge_features(const mjb_engine* e, int kind);
+int  mjb_ridge_gram(mjb_engine* e, int kind, double* out);
+int  mjb_ridge_predict(mjb_engine* e, int kind, const double* coeffs, double* sq_err);
+
 int  mjb_dev_vf_profile(mjb_engine* e, long long* out16, int enable);   /* enable: 1 arm, 0 read head CTA + disarm, 2 read K-split helper 0 */
 int  mjb_dev_lin_profile(mjb_engine* e, long long* out8, int enable);
 

@@ -49,6 +49,9 @@ _SIGNATURES = {
     "mjb_synchronize": (C.c_int, [_P]),
     "mjb_comm_unique_id": (C.c_int, [_P]),
     "mjb_comm_init": (C.c_int, [_P, _P]),
+    "mjb_ridge_features": (C.c_int, [_P, C.c_int]),
+    "mjb_ridge_gram": (C.c_int, [_P, C.c_int, _P]),
+    "mjb_ridge_predict": (C.c_int, [_P, C.c_int, _P, _P]),
     "mjb_p2p_export": (C.c_int, [_P, _P]),
     "mjb_p2p_import": (C.c_int, [_P, _P]),
     "mjb_p2p_enable": (C.c_int, [_P, C.c_int]),

@@ -173,6 +173,10 @@ class BatchREINFORCE:
             self.baseline.fit_defer()
         elif overlap:
             error_after = self.baseline.fit_end(return_errors=self.save_logs)
+        elif hasattr(self.baseline, "fit_resident"):      # ridge baselines: Gram pass over the resident batch + host solve
+            errs = self.baseline.fit_resident(eng, return_errors=self.save_logs)
+            if self.save_logs:
+                error_before, error_after = errs
         elif self.save_logs:
             error_before, error_after = self.baseline.fit(paths, return_errors=True)
         else:

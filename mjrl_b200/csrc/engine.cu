@@ -121,6 +121,12 @@ struct mjb_engine {
     unsigned long long** p2p_peer_dev = nullptr; int* p2p_seq = nullptr;
     long long p2p_slot = 0;
     bool p2p_ready = false, p2p_on = false;
+    // ---- ridge baselines (ridge.cu)
+    short2* ridge_ab = nullptr; int ridge_ab_kind = -1, ridge_K = 0;
+    double* ridge_partial = nullptr; size_t ridge_partial_cap = 0;
+    double* ridge_G = nullptr; size_t ridge_G_cap = 0;
+    double* ridge_coeff = nullptr; double* ridge_err = nullptr;
+    double* ridge_T = nullptr; size_t ridge_T_cap = 0;
     long long p2p_calls = 0;
     int* perm_dev = nullptr; long long perm_cap = 0;
     // global (all-rank) copies used by the replicated fit when world_size > 1
@@ -535,6 +541,8 @@ void mjb_destroy(mjb_engine* e) {
     if (e->comm) g_nccl.CommDestroy(e->comm);
     for (int p = 0; p < (int)e->p2p_peer.size(); ++p)
         if (p != e->cfg.rank && e->p2p_peer[p]) cudaIpcCloseMemHandle(e->p2p_peer[p]);
+    for (void* b : {(void*)e->ridge_ab, (void*)e->ridge_partial, (void*)e->ridge_G, (void*)e->ridge_coeff, (void*)e->ridge_err, (void*)e->ridge_T})
+        if (b) cudaFree(b);
     if (e->p2p_buf) cudaFree(e->p2p_buf);
     if (e->p2p_peer_dev) cudaFree(e->p2p_peer_dev);
     if (e->p2p_seq) cudaFree(e->p2p_seq);
@@ -728,6 +736,122 @@ int mjb_p2p_enable(mjb_engine* e, int on) {
 }
 
 long long mjb_p2p_calls(mjb_engine* e) { return e->p2p_calls; }
+
+// ------------------------------------------------------------------------ ridge baselines (Linear / Quadratic)
+// Feature columns in the reference's order (linear_baseline.py:19-36, quadratic_baseline.py:20-43):
+//   kind 0: [o (n) | 1 | al al^2 al^3 al^4]                      K = n + 5
+//   kind 1: [o (n) | o_i o_j, i <= j (n (n + 1) / 2) | 1 | al al^2 al^3 al^4]
+static int ridge_feature_count(int kind, int n) { return kind == 0 ? n + 5 : n + n * (n + 1) / 2 + 5; }
+static int ridge_setup(mjb_engine* e, int kind) {
+    const int n = e->cfg.obs_dim;
+    if (kind != 0 && kind != 1) FAIL(e, "ridge baseline kind must be 0 (linear) or 1 (quadratic)");
+    const int K = ridge_feature_count(kind, n);
+    if (K + 1 > 4096) FAIL(e, "ridge baseline: more than 4095 features (quadratic features of a wide observation)");
+    if (e->ridge_ab_kind == kind) return K;
+    std::vector<short2> ab;
+    const short ONE = (short)n, RET = (short)(n + 5);
+    for (int c = 0; c < n; ++c) ab.push_back(make_short2((short)c, ONE));
+    if (kind == 1)
+        for (int i = 0; i < n; ++i)
+            for (int j = i; j < n; ++j) ab.push_back(make_short2((short)i, (short)j));
+    ab.push_back(make_short2(ONE, ONE));
+    for (int k = 1; k <= 4; ++k) ab.push_back(make_short2((short)(n + k), ONE));
+    ab.push_back(make_short2(RET, ONE));                           // the augmented returns column (Gram launches only)
+    if (e->ridge_ab) cudaFree(e->ridge_ab);
+    CK(e, cudaMalloc(&e->ridge_ab, sizeof(short2) * ab.size()));
+    CK(e, cudaMemcpy(e->ridge_ab, ab.data(), sizeof(short2) * ab.size(), cudaMemcpyHostToDevice));
+    if (e->ridge_coeff) cudaFree(e->ridge_coeff);
+    CK(e, cudaMalloc(&e->ridge_coeff, sizeof(double) * (K + 1)));
+    if (!e->ridge_err) CK(e, cudaMalloc(&e->ridge_err, sizeof(double) * 2048));
+    e->ridge_ab_kind = kind; e->ridge_K = K;
+    return K;
+}
+
+// T = scaled observations | 1 | time powers | returns | 0 of the resident batch (ridge.cu); rebuilt per call: the batch or
+// its returns may have changed, and the pass is one write of n x (obs_dim + 7) doubles.
+static int ridge_scaled(mjb_engine* e, const RidgeArgs& a) {
+    const size_t need = (size_t)a.n * a.tile_cols;
+    if (need > e->ridge_T_cap) {
+        if (e->ridge_T) cudaFree(e->ridge_T);
+        e->ridge_T = nullptr; e->ridge_T_cap = 0;
+        CK(e, cudaMalloc(&e->ridge_T, sizeof(double) * need));
+        e->ridge_T_cap = need;
+    }
+    RidgeArgs b = a;
+    b.ret = e->ret;                                                // the returns column is always filled
+    if (launch_ridge_scale(b, e->ridge_T, e->stream) != cudaSuccess) FAIL(e, "ridge scale launch failed");
+    return 0;
+}
+
+int mjb_ridge_features(const mjb_engine* e, int kind) { return ridge_feature_count(kind, e->cfg.obs_dim); }
+
+// Gram matrix of [F | y] over the resident rollout batch (summed over the ranks): out = (K + 1) x (K + 1) doubles, row-major;
+// F^T F = out[:K, :K], F^T y = out[:K, K], y^T y = out[K, K].  Needs the returns (mjb_compute_returns / mjb_batch_set_returns).
+int mjb_ridge_gram(mjb_engine* e, int kind, double* out) {
+    const int K = ridge_setup(e, kind);
+    if (K < 0) return -1;
+    if (e->n_roll <= 0) FAIL(e, "mjb_ridge_gram: no rollout batch resident");
+    const int KA = K + 1;
+    RidgeArgs a;
+    a.obs = e->obs; a.tstep = e->tstep; a.ret = e->ret; a.n = e->n_roll; a.obs_dim = e->cfg.obs_dim;
+    a.K = KA; a.ab = e->ridge_ab; a.tile_cols = e->cfg.obs_dim + 7;
+    a.nb = ridge_blocks(KA);
+    const int npairs = a.nb * (a.nb + 1) / 2;
+    a.splits = (int)std::max<long long>(1, std::min<long long>({256LL, (2LL * e->num_sms + npairs - 1) / npairs, (e->n_roll + 255) / 256}));
+    if (KA <= 32) a.splits = (int)std::max<long long>(1, std::min<long long>(4LL * e->num_sms, (e->n_roll + 255) / 256));   // CTAs of 8 warps
+    const size_t need = KA <= 32 ? (size_t)a.splits * 8 * 1024 : (size_t)a.splits * npairs * 4096;
+    if (need > e->ridge_partial_cap) {
+        if (e->ridge_partial) cudaFree(e->ridge_partial);
+        CK(e, cudaMalloc(&e->ridge_partial, sizeof(double) * need));
+        e->ridge_partial_cap = need;
+    }
+    if ((size_t)KA * KA > e->ridge_G_cap) {
+        if (e->ridge_G) cudaFree(e->ridge_G);
+        CK(e, cudaMalloc(&e->ridge_G, sizeof(double) * (size_t)KA * KA));
+        e->ridge_G_cap = (size_t)KA * KA;
+    }
+    a.partial = e->ridge_partial;
+    if (ridge_scaled(e, a)) return -1;
+    const cudaError_t ce = launch_ridge_gram(a, e->ridge_T, e->ridge_G, e->stream);
+    if (ce != cudaSuccess) FAIL(e, std::string("ridge gram launch: ") + cudaGetErrorString(ce));
+    e->launches += 3;
+    if (allreduce(e, e->ridge_G, (size_t)KA * KA, ncclDouble)) return -1;
+    CK(e, cudaMemcpyAsync(out, e->ridge_G, sizeof(double) * (size_t)KA * KA, cudaMemcpyDeviceToHost, e->stream));
+    e->d2h_bytes += (long long)(sizeof(double) * (size_t)KA * KA);
+    CK(e, cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+// Predictions F c of every resident rollout sample into the baseline buffer (what mjb_compute_advantages reads and
+// mjb_batch_get(MJB_F_BASELINE) returns).  coeffs: K host doubles.  sq_err (nullable): sum over ALL ranks of (y - F c)^2.
+int mjb_ridge_predict(mjb_engine* e, int kind, const double* coeffs, double* sq_err) {
+    const int K = ridge_setup(e, kind);
+    if (K < 0) return -1;
+    if (e->n_roll <= 0) FAIL(e, "mjb_ridge_predict: no rollout batch resident");
+    if (copy_in(e, e->ridge_coeff, coeffs, sizeof(double) * K)) return -1;
+    RidgeArgs a;
+    a.obs = e->obs; a.tstep = e->tstep; a.ret = sq_err ? e->ret : nullptr; a.n = e->n_roll; a.obs_dim = e->cfg.obs_dim;
+    a.K = K; a.ab = e->ridge_ab; a.tile_cols = e->cfg.obs_dim + 7; a.partial = nullptr; a.splits = 0; a.nb = 0;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(2048, std::min<long long>(8LL * e->num_sms, (e->n_roll + 7) / 8)));
+    if (ridge_scaled(e, a)) return -1;
+    const cudaError_t ce = launch_ridge_predict(a, e->ridge_T, e->ridge_coeff, K, e->base, sq_err ? e->ridge_err : nullptr, grid, e->stream);
+    if (ce != cudaSuccess) FAIL(e, std::string("ridge predict launch: ") + cudaGetErrorString(ce));
+    e->launches += 2;
+    if (sq_err) {
+        std::vector<double> h(grid);
+        CK(e, cudaMemcpyAsync(h.data(), e->ridge_err, sizeof(double) * grid, cudaMemcpyDeviceToHost, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));
+        double s = 0.0;
+        for (int i = 0; i < grid; ++i) s += h[i];                  // fixed order
+        e->h_dsc[DS_VF] = s;
+        CK(e, cudaMemcpyAsync(e->dsc + DS_VF, e->h_dsc + DS_VF, sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        if (allreduce(e, e->dsc + DS_VF, 1, ncclDouble)) return -1;
+        CK(e, cudaMemcpyAsync(e->h_dsc + DS_VF, e->dsc + DS_VF, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        CK(e, cudaStreamSynchronize(e->stream));
+        *sq_err = e->h_dsc[DS_VF];
+    }
+    return 0;
+}
 
 // ---------------------------------------------------------------------------------------------- batch
 int mjb_vf_fit_end(mjb_engine* e, double* err_after);

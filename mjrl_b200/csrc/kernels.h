@@ -92,6 +92,20 @@ struct P2PReduceArgs {
     long long slot_words;
 };
 cudaError_t launch_reduce_allreduce_p2p(const P2PReduceArgs& a, cudaStream_t s);
+
+// ---- ridge.cu : Gram matrix / predictions of the ridge-regression baselines (Linear, Quadratic) on the resident batch
+struct RidgeArgs {
+    const float* obs; const int* tstep; const double* ret; long long n; int obs_dim;
+    int K;                        // features of the launch (Gram: the augmented count, features + returns column)
+    const short2* ab;             // [K] per feature: the two tile columns whose product it is
+    int tile_cols;                // obs_dim + 7: clip(o)/10 .., 1, al, al^2, al^3, al^4, y, 0
+    double* partial; int splits; int nb;   // Gram only: block partials [splits][nb (nb + 1) / 2][64][64], nb = ceil(K / 64)
+};
+int ridge_blocks(int K);
+cudaError_t launch_ridge_scale(const RidgeArgs& a, double* T, cudaStream_t s);      // T [n][tile_cols] float64
+cudaError_t launch_ridge_gram(const RidgeArgs& a, const double* T, double* G, cudaStream_t s);
+cudaError_t launch_ridge_predict(const RidgeArgs& a, const double* T, const double* coeff, int Kfeat, float* base,
+                                 double* err_partial, int grid, cudaStream_t s);
 // CG state lives on device: st = {rdotr, done_flag(as double), iters_run, g.x}
 // vscale2 (nullable): also emit the power-of-two scale {s, 1/s} of the new search direction p (tensor-core FVP)
 void launch_cg_init(const float* b, float* x, float* r, float* p, int d, double* st, float* vscale2, cudaStream_t s);

@@ -219,6 +219,27 @@ class Engine:
         else:
             self._ck(self.lib.mjb_vf_predict(self.h), "vf_predict")
 
+    # ------------------------------------------------------------------ ridge baselines (csrc/ridge.cu)
+    def ridge_features(self, kind):
+        return int(self.lib.mjb_ridge_features(self.h, int(kind)))
+
+    def ridge_gram(self, kind):
+        """Gram matrix of [features | returns] over the resident batch (all ranks): (F^T F [K,K], F^T y [K], y^T y)."""
+        K = self.ridge_features(kind)
+        out = np.empty((K + 1, K + 1), dtype=np.float64)
+        self._ck(self.lib.mjb_ridge_gram(self.h, int(kind), out.ctypes.data_as(C.c_void_p)), "ridge_gram")
+        return out[:K, :K].copy(), out[:K, K].copy(), float(out[K, K])
+
+    def ridge_predict(self, kind, coeffs, want_sq_err=False):
+        """features . coeffs for every resident sample into the device baseline buffer; optionally sum (returns - pred)^2."""
+        c = np.ascontiguousarray(coeffs, dtype=np.float64)
+        if c.shape != (self.ridge_features(kind),):
+            raise ValueError("ridge_predict: %d coefficients expected" % self.ridge_features(kind))
+        err = C.c_double(0.0)
+        self._ck(self.lib.mjb_ridge_predict(self.h, int(kind), c.ctypes.data_as(C.c_void_p),
+                                            C.byref(err) if want_sq_err else None), "ridge_predict")
+        return float(err.value) if want_sq_err else None
+
     def compute_advantages(self, gamma, gae_lambda):
         use_gae = gae_lambda is not None and 0.0 <= gae_lambda <= 1.0
         self._ck(self.lib.mjb_compute_advantages(self.h, float(gamma), float(gae_lambda) if use_gae else 0.0,

@@ -63,6 +63,9 @@ def advantages_on(eng, paths, baseline, gamma, gae_lambda=None, normalize=False,
             baseline._eng()                            # push the host weights if they changed
         eng.vf_predict(prefit=fit_in_flight)           # all paths in one launch (mlp_baseline.py:97-105)
         base = eng.baseline()
+    elif hasattr(baseline, "predict_resident"):        # ridge baselines: one launch over the resident batch
+        baseline.predict_resident(eng)
+        base = eng.baseline()
     else:                                              # any other baseline object keeps working on the host
         base = np.concatenate([np.asarray(baseline.predict(p), dtype=np.float32).ravel() for p in paths])
         eng.set_baseline(base)

@@ -75,5 +75,8 @@ def load():
     ns.EnvSpec, ns.MLP, ns.LinearPolicy, ns.MLPBaseline = EnvSpec, MLP, LinearPolicy, MLPBaseline
     ns.NPG, ns.TRPO, ns.DAPG, ns.BatchREINFORCE = NPG, TRPO, DAPG, BatchREINFORCE
     ns.cg_solve, ns.process_samples = cg_solve, process_samples
+    from mjrl.baselines.linear_baseline import LinearBaseline
+    from mjrl.baselines.quadratic_baseline import QuadraticBaseline
+    ns.LinearBaseline, ns.QuadraticBaseline = LinearBaseline, QuadraticBaseline
     _loaded = ns
     return ns
