@@ -1,4 +1,4 @@
-"""CPU tests of the N>1 host logic with the gloo backend (world_size 2): trajectory sharding, the unique-id
+"""CPU tests of the N>1 host logic with the gloo backend (world_size 2): trajectory sharding, the unique-id / IPC-handle exchange,
 broadcast helper, and the reduction semantics the engine relies on (sum of per-shard sums / global N -- not a
 mean of means -- reproduces the single-process gradient, FVP and whitening statistics)."""
 import os
@@ -115,6 +115,22 @@ def _worker(rank, world, port, out):
         owned = allreduce_sum_host(np.array([float(sum(len(p["rewards"]) for p in shard_paths(demo, world, rank)))]))
         assert int(owned[0]) == sum(len(p["rewards"]) for p in demo)
         assert shard_bounds([7], 2) == [(0, 1), (1, 1)]           # fewer paths than ranks: the last ranks stay empty
+        # ---- peer-memory all-reduce setup (engine.init_p2p): 64-byte IPC handles gathered in rank order; the fused kernel is
+        #      enabled only when EVERY rank could import (a rank on NCCL and one on peer memory would wait forever)
+        from mjrl_b200.parallel import all_gather_bytes, all_ranks_agree
+        handles = all_gather_bytes(bytes([rank + 1]) * 64, 64)
+        assert handles == [bytes([r + 1]) * 64 for r in range(world)]
+        assert all_ranks_agree(True) is True
+        assert all_ranks_agree(rank != 1) is False
+        # ---- ridge baselines (ridge.cu): the Gram matrix of [F | y] is additive over the shards
+        from oracle import ridge_oracle as RO
+        for p_ in paths:
+            p_["returns"] = O.discount_sum(p_["rewards"], 0.99)
+        for kind in (0, 1):
+            aug = lambda ps: np.concatenate([RO.features(ps, kind), cat(ps, "returns")[:, None]], axis=1)
+            Fl, Fa = aug(mine), aug(paths)
+            G = allreduce_sum_host(Fl.T.dot(Fl))
+            assert np.linalg.norm(G - Fa.T.dot(Fa)) / np.linalg.norm(Fa.T.dot(Fa)) < 1e-12
         out.put((rank, "ok"))
     except Exception as exc:      # surface the failure in the parent
         out.put((rank, repr(exc)))
