@@ -414,8 +414,10 @@ def run_gpu(args, cfg, rank, world, local_rank):
 
     def device_step():
         eng.compute_returns(GAMMA)
-        # host RNG draw, as optimize_model.py:22 (same order and RNG state as np.random.permutation(n), batched loops)
-        perm = runtime.global_permutation(n_glob)
+        # host RNG draw, as optimize_model.py:22 (same values and RNG state as np.random.permutation(n) per epoch); the call
+        # MLPBaseline.fit_begin makes: the NEXT step's draw is computed ahead on a worker thread and taken only if numpy's
+        # global RNG state is still the one it started from (tests/test_perm_speculation.py)
+        perm = runtime.global_permutations(n_glob, VF["epochs"])
         eng.vf_fit_begin(perm, VF["batch_size"], VF["learn_rate"], VF["reg_coef"])   # side stream: needs only the returns
         eng.vf_predict(prefit=True)           # pre-fit baseline, as in the reference's program order
         eng.compute_advantages(GAMMA, LAM)
@@ -583,6 +585,8 @@ def run_gpu(args, cfg, rank, world, local_rank):
                               else "nccl"),
             "wall_ms_per_step": wall / args.steps * 1e3, "phase_ms": phase, "trpo_backtracks": backtracks,
             "fit_us_per_adam_step": fit_us, "fit_adam_steps": fit_steps,
+            "fit_permutation": "np.random.permutation stream, one draw per epoch and step; computed ahead of use on a host worker "
+                               "thread and accepted only if numpy's global RNG state is unchanged (else drawn in place)",
             "roofline": roof, "roofline_hbm": hbm, "cpu_baseline": cpu, "trpo_backtrack_check": bt_check}
     print(json.dumps(line), flush=True)
     _exit_watchdog(60)

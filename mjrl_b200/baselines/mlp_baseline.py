@@ -196,7 +196,7 @@ class MLPBaseline:
         n_glob = eng.n_global()
         # host RNG draw at the reference's program point (optimize_model.py:22): one permutation per epoch, from
         # numpy's global RandomState (bit-identical order and RNG state, see runtime.global_permutation)
-        perms = np.stack([runtime.global_permutation(n_glob) for _ in range(self.epochs)])
+        perms = runtime.global_permutations(n_glob, self.epochs)
         return eng.vf_fit_begin(perms, self.batch_size, self.learn_rate, self.reg_coef, return_errors=return_errors)
 
     def fit_begin_resident(self, eng, return_errors=False):
@@ -206,7 +206,7 @@ class MLPBaseline:
         self._eng()
         assert eng.have_returns, "compute the returns on the engine first"
         n_glob = eng.n_global()
-        perms = np.stack([runtime.global_permutation(n_glob) for _ in range(self.epochs)])
+        perms = runtime.global_permutations(n_glob, self.epochs)
         return eng.vf_fit_begin(perms, self.batch_size, self.learn_rate, self.reg_coef, return_errors=return_errors)
 
     def fit_end(self, return_errors=False):

@@ -64,23 +64,86 @@ def get_engine(obs_dim, act_dim, hidden=None, vf_hidden=(128, 128), min_log_std=
     return eng
 
 
-def global_permutation(n):
-    """np.random.permutation(n) as int32, drawn from numpy's GLOBAL RandomState at this program point
-    (optimize_model.py:22) -- same order, same RNG state afterwards -- through the library's batched MT19937 /
-    Fisher-Yates loops (`mjb_host_permutation`), which are 2-3x faster than numpy's element-wise loop."""
+def _draw_permutations(key, pos, n, count):
+    """`count` consecutive np.random.permutation(n) draws from the MT19937 state (key, pos): returns (perms [count, n]
+    int32, key, pos) with the state advanced exactly as numpy would have (`mjb_host_permutation`, pinned against numpy in
+    tests/test_abi.py).  The foreign call releases the GIL."""
     import ctypes as C
     from mjrl_b200 import _native
+    lib = _native.load()
+    out = np.empty((count, n), dtype=np.int32)
+    cpos = C.c_int32(int(pos))
+    for i in range(count):
+        rc = lib.mjb_host_permutation(key.ctypes.data_as(C.c_void_p), C.byref(cpos), int(n), out[i].ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise RuntimeError("mjb_host_permutation failed (%d)" % rc)
+    return out, key, int(cpos.value)
+
+
+def _same_rng_state(a, b):
+    return a[0] == b[0] and int(a[2]) == int(b[2]) and int(a[3]) == int(b[3]) and float(a[4]) == float(b[4]) and \
+        np.array_equal(a[1], b[1])
+
+
+_speculation = None        # the permutations the NEXT fit will draw if nobody touches numpy's global RNG until then
+
+
+def _speculate(state, n, count):
+    """Start computing, on a worker thread and from a COPY of the RNG state, the `count` permutations the next fit of the
+    same size would draw.  They are used only if numpy's global state is still exactly `state` at that point."""
+    import os
+    import threading
+    global _speculation
+    if os.environ.get("MJRL_B200_PERM_SPECULATE", "1") == "0":
+        _speculation = None
+        return
+    box = {"snap": state, "n": int(n), "count": int(count), "result": None}
+
+    def work():
+        try:
+            key = np.array(state[1], dtype=np.uint32, copy=True, order="C")
+            box["result"] = _draw_permutations(key, int(state[2]), box["n"], box["count"])
+        except Exception:          # the regular draw will run (and raise, if it must) at the point of use
+            box["result"] = None
+
+    box["thread"] = threading.Thread(target=work, name="mjrl_b200-perm", daemon=True)
+    box["thread"].start()
+    _speculation = box
+
+
+def global_permutations(n, count=1, speculate_next=True):
+    """`count` x np.random.permutation(n) as int32 [count, n], drawn from numpy's GLOBAL RandomState at this program point
+    (optimize_model.py:22, one per epoch) -- same values, same RNG state afterwards -- through the library's batched
+    MT19937 / Fisher-Yates loops, which are 2-3x faster than numpy's element-wise loop.
+
+    The draw of 1e6 indices still costs ~5 ms of host time in front of the sequential fit chain, which is the critical
+    path of a train step.  So after every draw a worker thread computes, from a copy of the new RNG state, what the next
+    call with the same (n, count) would draw; the next call takes that result only if numpy's global state is
+    bit-for-bit the state the speculation started from (nobody drew a random number in between) and then installs the
+    advanced state.  Values and RNG stream are the reference's in every case; a miss just draws on the spot."""
+    global _speculation
     st = np.random.get_state()
+    n, count = int(n), int(count)
     if st[0] != "MT19937" or n < 2 or n > 0x7fffffff:
-        return np.random.permutation(np.arange(n, dtype=np.int32))
-    key = np.array(st[1], dtype=np.uint32, copy=True, order="C")
-    pos = C.c_int32(int(st[2]))
-    out = np.empty(n, dtype=np.int32)
-    rc = _native.load().mjb_host_permutation(key.ctypes.data_as(C.c_void_p), C.byref(pos), int(n), out.ctypes.data_as(C.c_void_p))
-    if rc != 0:
-        raise RuntimeError("mjb_host_permutation failed (%d)" % rc)
-    np.random.set_state(("MT19937", key, int(pos.value), st[3], st[4]))
-    return out
+        _speculation = None
+        return np.stack([np.random.permutation(np.arange(n, dtype=np.int32)) for _ in range(count)])
+    res, sp, _speculation = None, _speculation, None
+    if sp is not None:
+        sp["thread"].join()
+        if sp["result"] is not None and sp["n"] == n and sp["count"] == count and _same_rng_state(sp["snap"], st):
+            res = sp["result"]
+    if res is None:
+        res = _draw_permutations(np.array(st[1], dtype=np.uint32, copy=True, order="C"), int(st[2]), n, count)
+    perms, key, pos = res
+    np.random.set_state(("MT19937", key, pos, st[3], st[4]))
+    if speculate_next:
+        _speculate(np.random.get_state(), n, count)
+    return perms
+
+
+def global_permutation(n):
+    """One np.random.permutation(n) (int32) from numpy's global RandomState -- see global_permutations."""
+    return global_permutations(n, 1, speculate_next=False)[0]
 
 
 class session:
