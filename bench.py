@@ -96,6 +96,12 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        late = False
+        if not self.rows:                      # a timed region shorter than nvidia-smi's start-up (cfg1: 6 ms): take the first
+            t0 = time.time()                   # sample it delivers, i.e. the clocks right after the region, and say so
+            while not self.rows and time.time() - t0 < 1.5:
+                time.sleep(0.02)
+            late = True
         self.proc.terminate()
         sm, mx, reasons, pw = [], [], set(), []
         for r in self.rows:
@@ -109,8 +115,11 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+        if late:
+            out["note"] = "timed region shorter than the sampler's start-up: first sample taken right after it"
+        return out
 
 
 def load_peaks():
@@ -512,7 +521,7 @@ def run_gpu(args, cfg, rank, world, local_rank):
         raise SystemExit("no FVP kernel timing was recorded inside the timed steps (fvp_kernel_ms = %r)" % fvp_ms_kernel)
     prof = {}
     pj = os.path.join(ROOT, "profiles", "fvp_ncu_%s.json" % args.config)
-    if os.path.exists(pj):
+    if os.path.exists(pj) and world == 1:                # the ncu capture is of a 1-GPU launch: no traffic figure for a shard
         prof = json.load(open(pj))
     if linear:
         roof = {"bound": "hbm", "achieved": by / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -526,6 +535,8 @@ def run_gpu(args, cfg, rank, world, local_rank):
     if linear:
         kname = ("linear_tc_kernel (tcgen05 kind::f16, M=128 stacked fp16 hi/lo rows, TMEM-resident gradient accumulators)"
                  if tc_active else "linear_kernel<AG,MODE_FVP> (fp32 FMA)")
+        if tc_active and cfg["obs"] % 4 == 0:
+            kname = kname.replace("linear_tc_kernel", "linear_tc_tma_kernel (TMA-fed fp32 ring, warp-specialised)")
     else:
         kname = ("fvp_tc_kernel (tcgen05 kind::f16, two-term fp16 split = 3 MMAs per logical product, TMEM accumulators)"
                  if tc_active else "mlp_kernel<H,MT,MODE_FVP> (fp32 FMA)")
